@@ -1,0 +1,194 @@
+/*
+ * wfk_b200.h -- C ABI of libwfk_b200.so: the B200 (sm_100a) kernels behind the Path-B latent
+ * nowcast rollout and its scoring.
+ *
+ * The reference (Autobot37/weatherforecastingtoolkit) has NO native layer: its boundary for this
+ * path is plain Python. Every entry point below therefore cites the
+ * reference PyTorch call site it replaces (paths relative to the reference repo root). The
+ * reference-side binding a maintainer would add is the ctypes shim shown in INTEGRATION.md
+ * (shipped as weatherforecastingtoolkit_b200/_cabi.py).
+ *
+ * Conventions: plain pointers and sizes only; all data pointers are DEVICE pointers to contiguous
+ * buffers owned by the caller unless a parameter says "host"; `stream` is a cudaStream_t passed as
+ * void*; every call only enqueues work on that stream (no hidden synchronisation) and returns 0 on
+ * success or a negative wfk_status. There is no CPU fallback: an unsupported shape is an error.
+ */
+#ifndef WFK_B200_H
+#define WFK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFK_ABI_VERSION 1
+
+enum wfk_status {
+  WFK_OK = 0,
+  WFK_ERR_INVALID = -1,     /* bad argument / unsupported shape                      */
+  WFK_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed (see wfk_last_error) */
+  WFK_ERR_NO_DEVICE = -3,   /* no sm_100 device visible                              */
+  WFK_ERR_NOT_INIT = -4     /* wfk_init has not been called                          */
+};
+
+const char* wfk_strerror(int status);
+const char* wfk_last_error(void);     /* detail string of the most recent failure (thread-local) */
+int wfk_abi_version(void);
+/* Select the device, check compute capability 10.x, resolve cuTensorMapEncodeTiled. */
+int wfk_init(int device);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t wfk_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  VIL frame staging.  Replaces SEVIRDataLoader.preprocess_data_dict + change_layout
+ *     (pipeline/datasets/sevir/sevir.py:626-666, 88-101; uint8->float cast at :587-592):
+ *     out[n,t,0,h,w] = fl32(1/255) * (float)in[n,h,w,t], NHWT uint8 -> N T C H W.
+ *     out_dtype: 0 = float32, 1 = float16 (round-to-nearest-even of the fp32 value).
+ */
+int wfk_stage_vil_u8(const uint8_t* nhwt, int n, int h, int w, int t, void* out_ntchw, int out_dtype,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a8  Latent predictor.  Replaces the residual framing + nn.Linear(13*C, 12*C) + permutes of
+ *     Model.validation_step (experiments/v1_experiments/pretrained_ae_linear_sevir/train.py:
+ *     67, 101-113).  lat [B, t_in+t_out, C, HW] fp32 (HW = latent pixels); weight [t_out*C, t_in*C],
+ *     bias [t_out*C] fp32.  Writes pred [B, t_out, C, HW] (= Linear(inp - last) + last) and, when
+ *     non-NULL, tgt [B, t_out, C, HW] (copy of lat[:, t_in:]) and loss_sums[2] (double:
+ *     sum((pred-tgt)^2), element count) -- the val_loss of train.py:109 is loss_sums[0]/loss_sums[1].
+ *     loss_sums must be zeroed by the caller.
+ */
+int wfk_predict_linear(const float* lat, const float* weight, const float* bias, int b, int t_in, int t_out,
+                       int c, int hw, float* pred, float* tgt, double* loss_sums, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a10-a14  Fused skill-score pass.  Replaces the 41 passes of calc_metrics
+ *     (pipeline/metrics.py:86-133): clamp(0,1) (:92-93); _hit_miss_fa_cn counts (:9-16) at the
+ *     fp32 thresholds for pools none / avg4 / avg16 (csi :43-54, hss :56-69, avg_pool2d :46-50);
+ *     crps == MAE at one member (:18-41); torchmetrics SSIM (:71-75) and per-frame PSNR (:77-84).
+ */
+#define WFK_MAX_THRESHOLDS 8
+#define WFK_NUM_POOLS 3 /* pool 1, 4, 16 */
+
+typedef struct wfk_metric_partials {
+  /* exact integer contingency counts over all frames: [pool][threshold][tp, fn, fp, tn] */
+  int64_t counts[WFK_NUM_POOLS][WFK_MAX_THRESHOLDS][4];
+  int64_t n_elems[WFK_NUM_POOLS]; /* pixels (pooled cells) counted per pool                  */
+  int64_t n_frames;               /* frames scored                                            */
+  double abs_sum[WFK_NUM_POOLS];  /* sum |pred - tgt| of the (pooled) clamped fields         */
+  double sq_sum;                  /* sum (pred - tgt)^2, pool 1                               */
+  double ssim_sum;                /* sum over frames of the per-frame mean SSIM               */
+  double psnr_sum;                /* sum over frames of 10*log10(range^2 / mse_frame)         */
+  double reserved[2];
+} wfk_metric_partials;
+
+size_t wfk_metrics_workspace_bytes(int frames, int h, int w);
+/* pred, tgt: [frames, h, w] fp32 (any values; clamped inside). thresholds: HOST array of fp32
+ * values (already rounded the way torch rounds the Python-float threshold, SURVEY hazard H2).
+ * out: DEVICE struct, fully overwritten. workspace: DEVICE scratch of workspace_bytes. */
+int wfk_metrics(const float* pred, const float* tgt, int frames, int h, int w, const float* thresholds,
+                int n_thresholds, wfk_metric_partials* out, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3-a6, a9  Autoencoder building blocks (activations NHWC fp16 on device).
+ *
+ * Implicit-GEMM convolution / GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * Replaces nn.Conv2d 3x3 / 1x1 (resnet.py:405,421,452; vae.py:24,68,103,148), Downsample2D
+ * (resnet.py:181-190), Upsample2D (resnet.py:108-143), the residual add (resnet.py:493) and the
+ * attention linears / baddbmm / bmm (attention.py:146-176), and accumulates the GroupNorm
+ * statistics of its own output (resnet.py:403,419) in the epilogue.
+ *
+ * One launch computes, for every output tile (128 pixels x BN channels),
+ *     D = sum over taps  A_src[pixel + (dx,dy), k-range] * B_src[slab, n, k-range]
+ * followed by  out = D + bias (+ residual), optional fp16 / fp32 stores and per-(frame, group)
+ * sum / sum-of-squares accumulation.
+ */
+typedef struct wfk_tap {
+  int8_t dx, dy;    /* pixel offset added to the tile origin (x, y coordinate of the A view)   */
+  int8_t q;         /* coordinate of the auxiliary A dimension (0 unless a phase/parity view)   */
+  int8_t src;       /* which A / B source pair (0 or 1)                                         */
+  int16_t c_off;    /* starting element along the innermost A dimension                         */
+  int16_t b_slab;   /* slab (3rd coordinate) of the B source                                    */
+  int16_t kblocks;  /* number of 64-element K blocks this tap contributes                       */
+  int16_t reserved;
+} wfk_tap;
+
+/* A view: 5-D, innermost first: (k, x, q, y, frame); strides in BYTES (stride[0] is implied). */
+typedef struct wfk_view5 {
+  const void* ptr;
+  int64_t dim[5];
+  int64_t stride[5];
+} wfk_view5;
+/* B view: 3-D: (k, n, slab). */
+typedef struct wfk_view3 {
+  const void* ptr;
+  int64_t dim[3];
+  int64_t stride[3];
+} wfk_view3;
+
+#define WFK_MAX_TAPS 40
+
+typedef struct wfk_conv_desc {
+  wfk_view5 a[2];
+  wfk_view3 b[2];
+  int32_t n_frames;      /* tiles are enumerated per frame                                      */
+  int32_t tile_h, tile_w;/* extent of the tile coordinate space (rows, cols of output pixels per phase) */
+  int32_t n_total;       /* GEMM N (output channels); multiple of 8 (of the N tile when stats)   */
+  int32_t num_phases;    /* 1, or 4 for the sub-pixel (nearest x2 upsample) decomposition        */
+  int32_t taps_per_phase;
+  wfk_tap taps[WFK_MAX_TAPS]; /* [phase][tap]                                                    */
+  int32_t a_frame_mul;   /* A frame coordinate = frame * a_frame_mul  (0: A shared by all frames) */
+  int32_t b_frame_mul;   /* B slab coordinate  = tap.b_slab + frame * b_frame_mul                */
+  const float* bias;     /* [n_total] or NULL                                                   */
+  const void* residual;  /* fp16, same addressing as out, or NULL                               */
+  void* out_h;           /* fp16 output or NULL                                                 */
+  float* out_f;          /* fp32 output or NULL                                                 */
+  double* stats;         /* [n_frames][n_total/cpg][2] accumulators (caller-zeroed) or NULL     */
+  int32_t out_rows, out_cols; /* output tensor spatial dims                                     */
+  int32_t out_sy, out_sx;/* output pixel = (y*out_sy + (phase>>1), x*out_sx + (phase&1))         */
+  int32_t ldc;           /* output / residual channel pitch in elements                         */
+  int32_t cpg;           /* channels per GroupNorm group (4, 8 or 16) when stats != NULL        */
+  int32_t operand_bf16;  /* 0: fp16 operands (default), 1: bf16 operands                        */
+} wfk_conv_desc;
+
+typedef struct wfk_conv_plan wfk_conv_plan;
+int wfk_conv_plan_create(const wfk_conv_desc* desc, wfk_conv_plan** out);
+int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream);
+void wfk_conv_plan_destroy(wfk_conv_plan* plan);
+
+/* GroupNorm apply (+ optional SiLU).  Replaces nn.GroupNorm(32, C, eps=1e-6) + SiLU
+ * (resnet.py:457-458, 479-485; vae.py:82-83, 162-163; attention.py:141).  x, out: [n, hw, c] fp16;
+ * stats: [n][groups][2] double (sum, sum of squares over the group's c/groups * hw values). */
+int wfk_groupnorm_apply(const void* x, const double* stats, const float* gamma, const float* beta, int n,
+                        int hw, int c, int groups, float eps, int apply_silu, void* out, void* stream);
+
+/* Direct 3x3 (pad 1, stride 1) convolution for tiny input-channel counts.  Replaces
+ * encoder.conv_in (vae.py:24) and post_quant_conv + decoder.conv_in (autoencoder_kl.py:87,
+ * vae.py:103).  in: [n, cin, h, w] fp32 NCHW; optional pre 1x1 conv (pre_w [cin,cin], pre_b [cin])
+ * applied to in-bounds taps; w: [cout, cin, 3, 3] fp32; out: [n, h, w, cout] fp16 + stats. */
+int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int w, const float* pre_w,
+                          const float* pre_b, const float* weight, const float* bias, int cout, void* out,
+                          double* stats, int cpg, void* stream);
+
+/* Direct 3x3 (pad 1, stride 1) convolution for tiny output-channel counts, optional post 1x1.
+ * Replaces decoder.conv_out (vae.py:148) and encoder.conv_out + quant_conv (vae.py:68,
+ * autoencoder_kl.py:82).  in: [n, h, w, cin] fp16 (already normalised + SiLU); weight_h:
+ * [cout][9][cin] fp16; bias [cout]; post_w [cout,cout], post_b [cout] or NULL; out [n, cout, h, w] fp32. */
+int wfk_conv3x3_small_cout(const void* in, int n, int h, int w, int cin, const void* weight_h,
+                           const float* bias, int cout, const float* post_w, const float* post_b, float* out,
+                           void* stream);
+
+/* Row softmax: probs[r, :] = softmax(scale * scores[r, :]) in fp32, stored fp16.
+ * Replaces torch.softmax(attention_scores.float(), dim=-1) (attention.py:171); `scale` is the
+ * baddbmm alpha (attention.py:148, 168). */
+int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, void* stream);
+
+/* fp32 -> fp16 conversion of weights at pack time (device to device). */
+int wfk_f32_to_f16(const float* in, int64_t n, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFK_B200_H */

@@ -1,0 +1,537 @@
+// Implicit-GEMM convolution / GEMM for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+// Data layout: activations NHWC fp16 (channels innermost) so that a tile of 128 output pixels x 64
+// input channels is a TMA box (64, BW, 1, BH, 1) of the 5-D view (k, x, q, y, frame); TMA writes it
+// as 128 rows of 128 B with the 128-byte swizzle, which is exactly the K-major operand layout
+// tcgen05.mma reads. A 3x3 convolution is 9 "taps": the same box shifted by (dx, dy); rows that fall
+// outside the image are zero-filled by TMA, which implements the convolution's zero padding.
+// Weights are [slab][cout][cin] fp16 and arrive as the box (64, BN, 1) of the 3-D view (k, n, slab).
+//
+// Warp roles (192 threads, one persistent CTA per SM):
+//   warp 0      : TMA producer (one elected lane)       -- fills the STAGES-deep smem ring
+//   warp 1      : TMEM allocator + MMA issuer (one lane) -- 4 x tcgen05.mma (K=16) per 64-wide K block
+//   warps 2..5  : epilogue -- tcgen05.ld the 128 x BN fp32 accumulator, + bias (+ residual),
+//                 GroupNorm sum / sum-of-squares of the result, fp16 / fp32 stores
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+// the MMAs of tile i+1.
+//
+// Replaces (reference, all cuDNN / cuBLAS library calls): nn.Conv2d 3x3 / 1x1
+// (pipeline/models/autoencoderkl/resnet.py:405,421,452), Downsample2D (resnet.py:181-190),
+// Upsample2D (resnet.py:108-143), the attention linears and bmm's (attention.py:146-176).
+#include <new>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace wfk {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // fp16 elements = one 128 B swizzle row
+constexpr int kConvThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 2;
+
+struct ConvKernelParams {
+  CUtensorMap a_map[2];
+  CUtensorMap b_map[2];
+  int n_frames, tile_h, tile_w, tiles_x, tiles_y, tiles_n, n_total;
+  int bw_log2;
+  int num_phases, taps_per_phase;
+  int a_frame_mul, b_frame_mul;
+  const float* bias;
+  const __half* residual;
+  __half* out_h;
+  float* out_f;
+  double* stats;
+  int out_rows, out_cols, out_sy, out_sx, ldc;
+  int cpg_log2, groups_total;
+  uint32_t idesc;
+  wfk_tap taps[WFK_MAX_TAPS];
+};
+
+struct TileCoord {
+  int phase, frame, ty, tx, nt;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int tile) {
+  TileCoord t;
+  const int per_frame = p.tiles_y * p.tiles_x;
+  const int per_phase = p.n_frames * per_frame * p.tiles_n;
+  t.phase = tile / per_phase;
+  int r = tile - t.phase * per_phase;
+  const int mt = r / p.tiles_n;
+  t.nt = r - mt * p.tiles_n;
+  t.frame = mt / per_frame;
+  r = mt - t.frame * per_frame;
+  t.ty = r / p.tiles_x;
+  t.tx = r - t.ty * p.tiles_x;
+  return t;
+}
+
+// Sum / sum-of-squares of 32 consecutive channels (one accumulator row chunk per lane) reduced over
+// the 32 lanes (pixels) of the warp for each of NG = 32/cpg groups, with a transposing butterfly:
+// after log2(NG) exchange steps every lane owns one group, then a plain xor-reduction finishes.
+template <int NG>
+__device__ __forceinline__ void chunk_group_stats(const float (&v)[32], bool valid, int lane, float* s_dst) {
+  constexpr int CPG = 32 / NG;
+  float s[NG], q[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      const float x = v[g * CPG + j];
+      a += x;
+      b = fmaf(x, x, b);
+    }
+    s[g] = valid ? a : 0.f;
+    q[g] = valid ? b : 0.f;
+  }
+  int grp = 0;
+#pragma unroll
+  for (int n = NG, off = 16; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+    grp += upper ? (n >> 1) : 0;
+#pragma unroll
+    for (int i = 0; i < (n >> 1); ++i) {
+      const float ks = upper ? s[i + (n >> 1)] : s[i];
+      const float ss = upper ? s[i] : s[i + (n >> 1)];
+      const float kq = upper ? q[i + (n >> 1)] : q[i];
+      const float sq = upper ? q[i] : q[i + (n >> 1)];
+      s[i] = ks + __shfl_xor_sync(0xffffffffu, ss, off);
+      q[i] = kq + __shfl_xor_sync(0xffffffffu, sq, off);
+    }
+  }
+  constexpr int REM = 32 / NG;  // lanes that still hold partials of the same group
+#pragma unroll
+  for (int off = REM >> 1; off >= 1; off >>= 1) {
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], off);
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], off);
+  }
+  if ((lane & (REM - 1)) == 0) {
+    atomicAdd(&s_dst[2 * grp + 0], s[0]);
+    atomicAdd(&s_dst[2 * grp + 1], q[0]);
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [BN/4 groups max][2]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map[0]);
+    tma_prefetch_desc(&p.b_map[0]);
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int total_tiles = p.num_phases * p.n_frames * p.tiles_y * p.tiles_x * p.tiles_n;
+  const int bw = 1 << p.bw_log2;
+  const int bh = kBlockM >> p.bw_log2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int x0 = t.tx * bw, y0 = t.ty * bh;
+        for (int ti = 0; ti < p.taps_per_phase; ++ti) {
+          const wfk_tap tap = p.taps[t.phase * p.taps_per_phase + ti];
+          const CUtensorMap* am = &p.a_map[tap.src];
+          const CUtensorMap* bm = &p.b_map[tap.src];
+          for (int kb = 0; kb < tap.kblocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_5d(sa, am, &full_bar[stage], tap.c_off + kb * kBlockK, x0 + tap.dx, tap.q, y0 + tap.dy,
+                        t.frame * p.a_frame_mul);
+            tma_load_3d(sa + kABytes, bm, &full_bar[stage], kb * kBlockK, t.nt * BN,
+                        tap.b_slab + t.frame * p.b_frame_mul);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        uint32_t accumulate = 0;
+        for (int ti = 0; ti < p.taps_per_phase; ++ti) {
+          const int kblocks = p.taps[t.phase * p.taps_per_phase + ti].kblocks;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+            const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
+                       accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5)
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;       // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool do_stats = p.stats != nullptr;
+    if (do_stats) {
+      for (int i = et; i < BN / 2; i += 128) s_stats[i] = 0.f;
+      named_bar_sync(1, 128);
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int row = quarter * 32 + lane;
+      const int py = t.ty * bh + (row >> p.bw_log2);
+      const int px = t.tx * bw + (row & (bw - 1));
+      const bool valid = (py < p.tile_h) && (px < p.tile_w);
+      const int oy = py * p.out_sy + (t.phase >> 1);
+      const int ox = px * p.out_sx + (t.phase & 1);
+      const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
+      const int64_t base = pix * p.ldc + static_cast<int64_t>(t.nt) * BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
+
+      const int ncols = min(BN, p.n_total - t.nt * BN);  // N tail: columns >= ncols are padding
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_wait();
+        const int nvec = min(4, (ncols - c0) >> 3);  // valid 8-channel vectors in this chunk
+        float v[32];
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + t.nt * BN + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = (j < 2 * nvec) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (p.residual != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + base + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nvec) {
+              const uint4 u = __ldg(rp + j);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                v[8 * j + 2 * e + 0] += f.x;
+                v[8 * j + 2 * e + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (do_stats) {
+          float* dst = s_stats + 2 * (c0 >> p.cpg_log2);
+          if (p.cpg_log2 == 2) chunk_group_stats<8>(v, valid, lane, dst);
+          else if (p.cpg_log2 == 3) chunk_group_stats<4>(v, valid, lane, dst);
+          else chunk_group_stats<2>(v, valid, lane, dst);
+        }
+        if (valid) {
+          if (p.out_h != nullptr) {
+            uint4* op = reinterpret_cast<uint4*>(p.out_h + base + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < nvec) {
+                uint4 u;
+                __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                op[j] = u;
+              }
+            }
+          }
+          if (p.out_f != nullptr) {
+            float4* op = reinterpret_cast<float4*>(p.out_f + base + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < 2 * nvec) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+
+      if (do_stats) {
+        named_bar_sync(1, 128);
+        const int groups_in_tile = BN >> p.cpg_log2;
+        if (et < 2 * groups_in_tile) {
+          const int g = ((t.nt * BN) >> p.cpg_log2) + (et >> 1);
+          atomicAdd(&p.stats[(static_cast<int64_t>(t.frame) * p.groups_total + g) * 2 + (et & 1)],
+                    static_cast<double>(s_stats[et]));
+          s_stats[et] = 0.f;
+        }
+        named_bar_sync(1, 128);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+template <int BN>
+struct ConvCfg;
+template <>
+struct ConvCfg<256> {
+  static constexpr int kStages = 4;
+};
+template <>
+struct ConvCfg<128> {
+  static constexpr int kStages = 6;
+};
+
+template <int BN>
+constexpr size_t conv_smem_bytes() {
+  return 1024 /*align slack*/ + ConvCfg<BN>::kStages * (kABytes + BN * kBlockK * 2) + (2 * ConvCfg<BN>::kStages + 4) * 8 +
+         16 + (BN / 2) * 4 + 64;
+}
+
+}  // namespace wfk
+
+struct wfk_conv_plan {
+  wfk::ConvKernelParams params;
+  int bn;
+  int grid;
+};
+
+namespace {
+
+int encode_a(const wfk_view5& v, int bw, int bh, bool bf16, CUtensorMap* out) {
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(wfk::kBlockK), static_cast<cuuint32_t>(bw), 1u,
+                       static_cast<cuuint32_t>(bh), 1u};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) dims[i] = static_cast<cuuint64_t>(v.dim[i]);
+  for (int i = 1; i < 5; ++i) strides[i - 1] = static_cast<cuuint64_t>(v.stride[i]);
+  CUresult r = wfk::g_encode_tiled(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
+                                   const_cast<void*>(v.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return wfk::fail(WFK_ERR_CUDA,
+                     "cuTensorMapEncodeTiled(A) failed: %d dims=(%lld,%lld,%lld,%lld,%lld) strides=(%lld,%lld,%lld,%lld) "
+                     "box=(64,%d,1,%d,1)",
+                     (int)r, (long long)v.dim[0], (long long)v.dim[1], (long long)v.dim[2], (long long)v.dim[3],
+                     (long long)v.dim[4], (long long)v.stride[1], (long long)v.stride[2], (long long)v.stride[3],
+                     (long long)v.stride[4], bw, bh);
+  return WFK_OK;
+}
+
+int encode_b(const wfk_view3& v, int bn, bool bf16, CUtensorMap* out) {
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(wfk::kBlockK), static_cast<cuuint32_t>(bn), 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  for (int i = 0; i < 3; ++i) dims[i] = static_cast<cuuint64_t>(v.dim[i]);
+  for (int i = 1; i < 3; ++i) strides[i - 1] = static_cast<cuuint64_t>(v.stride[i]);
+  CUresult r = wfk::g_encode_tiled(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                                   const_cast<void*>(v.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return wfk::fail(WFK_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d dims=(%lld,%lld,%lld) strides=(%lld,%lld)",
+                     (int)r, (long long)v.dim[0], (long long)v.dim[1], (long long)v.dim[2], (long long)v.stride[1],
+                     (long long)v.stride[2]);
+  return WFK_OK;
+}
+
+int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return ((1 << l) == v) ? l : -1;
+}
+
+}  // namespace
+
+extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(d != nullptr && out != nullptr, "null argument");
+  WFK_REQUIRE(d->n_total > 0 && d->n_total % 8 == 0, "n_total=%d must be a positive multiple of 8", d->n_total);
+  WFK_REQUIRE(d->num_phases == 1 || d->num_phases == 4, "num_phases must be 1 or 4");
+  WFK_REQUIRE(d->taps_per_phase >= 1 && d->num_phases * d->taps_per_phase <= WFK_MAX_TAPS, "too many taps");
+  WFK_REQUIRE(d->n_frames >= 1 && d->tile_h >= 1 && d->tile_w >= 1, "empty problem");
+  WFK_REQUIRE(d->a[0].ptr != nullptr && d->b[0].ptr != nullptr, "A/B source 0 missing");
+  WFK_REQUIRE(d->out_h != nullptr || d->out_f != nullptr, "no output requested");
+  WFK_REQUIRE(d->ldc % 8 == 0, "ldc must be a multiple of 8");
+  bool uses_src1 = false;
+  for (int i = 0; i < d->num_phases * d->taps_per_phase; ++i) {
+    const wfk_tap& t = d->taps[i];
+    WFK_REQUIRE(t.src == 0 || t.src == 1, "tap %d: bad src", i);
+    WFK_REQUIRE(t.kblocks >= 1, "tap %d: kblocks must be >= 1", i);
+    WFK_REQUIRE(t.c_off % 8 == 0, "tap %d: c_off must be a multiple of 8", i);
+    uses_src1 |= (t.src == 1);
+  }
+  if (uses_src1) WFK_REQUIRE(d->a[1].ptr != nullptr && d->b[1].ptr != nullptr, "A/B source 1 missing");
+  int cpg_log2 = 0;
+  if (d->stats != nullptr) {
+    cpg_log2 = ilog2_exact(d->cpg);
+    WFK_REQUIRE(cpg_log2 >= 2 && cpg_log2 <= 4, "cpg=%d must be 4, 8 or 16 when stats are requested", d->cpg);
+  }
+
+  wfk_conv_plan* plan = new (std::nothrow) wfk_conv_plan();
+  WFK_REQUIRE(plan != nullptr, "out of memory");
+  wfk::ConvKernelParams& p = plan->params;
+  plan->bn = (d->n_total % 256 == 0 || d->n_total > 256) ? 256 : 128;
+  if (d->stats != nullptr && d->n_total % plan->bn != 0) {
+    delete plan;
+    return wfk::fail(WFK_ERR_INVALID, "stats need n_total (%d) to be a multiple of the N tile (%d)", d->n_total, plan->bn);
+  }
+
+  // tile geometry: BW x BH = 128 output pixels, BW a power of two; minimise the padded area
+  int best_log2 = 7;
+  long best_area = -1;
+  for (int l = 7; l >= 3; --l) {
+    const int bw = 1 << l, bh = 128 >> l;
+    const long area = static_cast<long>((d->tile_w + bw - 1) / bw) * bw * (static_cast<long>((d->tile_h + bh - 1) / bh) * bh);
+    if (best_area < 0 || area < best_area) {
+      best_area = area;
+      best_log2 = l;
+    }
+  }
+  const int bw = 1 << best_log2, bh = 128 >> best_log2;
+  p.bw_log2 = best_log2;
+  p.n_frames = d->n_frames;
+  p.tile_h = d->tile_h;
+  p.tile_w = d->tile_w;
+  p.tiles_x = (d->tile_w + bw - 1) / bw;
+  p.tiles_y = (d->tile_h + bh - 1) / bh;
+  p.tiles_n = (d->n_total + plan->bn - 1) / plan->bn;
+  p.n_total = d->n_total;
+  p.num_phases = d->num_phases;
+  p.taps_per_phase = d->taps_per_phase;
+  p.a_frame_mul = d->a_frame_mul;
+  p.b_frame_mul = d->b_frame_mul;
+  p.bias = d->bias;
+  p.residual = static_cast<const __half*>(d->residual);
+  p.out_h = static_cast<__half*>(d->out_h);
+  p.out_f = d->out_f;
+  p.stats = d->stats;
+  p.out_rows = d->out_rows;
+  p.out_cols = d->out_cols;
+  p.out_sy = d->out_sy;
+  p.out_sx = d->out_sx;
+  p.ldc = d->ldc;
+  p.cpg_log2 = cpg_log2;
+  p.groups_total = d->stats ? (d->n_total >> cpg_log2) : 0;
+  p.idesc = wfk::umma_idesc_f16(128, static_cast<uint32_t>(plan->bn), d->operand_bf16 ? 1u : 0u);
+  for (int i = 0; i < WFK_MAX_TAPS; ++i) p.taps[i] = d->taps[i];
+
+  int rc = encode_a(d->a[0], bw, bh, d->operand_bf16 != 0, &p.a_map[0]);
+  if (rc == WFK_OK) rc = encode_b(d->b[0], plan->bn, d->operand_bf16 != 0, &p.b_map[0]);
+  if (rc == WFK_OK && uses_src1) {
+    rc = encode_a(d->a[1], bw, bh, d->operand_bf16 != 0, &p.a_map[1]);
+    if (rc == WFK_OK) rc = encode_b(d->b[1], plan->bn, d->operand_bf16 != 0, &p.b_map[1]);
+  } else if (rc == WFK_OK) {
+    p.a_map[1] = p.a_map[0];
+    p.b_map[1] = p.b_map[0];
+  }
+  if (rc != WFK_OK) {
+    delete plan;
+    return rc;
+  }
+  const long total_tiles = static_cast<long>(p.num_phases) * p.n_frames * p.tiles_y * p.tiles_x * p.tiles_n;
+  if (total_tiles > 0x7fffffffL) {
+    delete plan;
+    return wfk::fail(WFK_ERR_INVALID, "too many tiles");
+  }
+  plan->grid = static_cast<int>(total_tiles < wfk::g_num_sms ? total_tiles : wfk::g_num_sms);
+  *out = plan;
+  return WFK_OK;
+}
+
+extern "C" int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(plan != nullptr, "null plan");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv_gemm_kernel<256, wfk::ConvCfg<256>::kStages>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(wfk::conv_smem_bytes<256>())));
+    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv_gemm_kernel<128, wfk::ConvCfg<128>::kStages>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(wfk::conv_smem_bytes<128>())));
+    attr_set = true;
+  }
+  if (plan->bn == 256) {
+    wfk::conv_gemm_kernel<256, wfk::ConvCfg<256>::kStages>
+        <<<plan->grid, wfk::kConvThreads, wfk::conv_smem_bytes<256>(), s>>>(plan->params);
+  } else {
+    wfk::conv_gemm_kernel<128, wfk::ConvCfg<128>::kStages>
+        <<<plan->grid, wfk::kConvThreads, wfk::conv_smem_bytes<128>(), s>>>(plan->params);
+  }
+  return wfk::launched("conv_gemm_kernel");
+}
+
+extern "C" void wfk_conv_plan_destroy(wfk_conv_plan* plan) { delete plan; }

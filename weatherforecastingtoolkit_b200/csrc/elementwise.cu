@@ -1,0 +1,132 @@
+// HBM-bound passes between the tensor-core kernels: GroupNorm apply (+SiLU), row softmax,
+// fp32 -> fp16 weight conversion. All use 128-bit vector loads/stores on NHWC fp16 activations.
+#include <cuda_fp16.h>
+
+#include "internal.h"
+
+namespace wfk {
+
+// y = silu?( (x - mean) * rstd * gamma + beta ), with mean / rstd from the (sum, sumsq) pairs the
+// producing kernel accumulated. One block = `ppb` pixels of one frame, all channels.
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int hw, int c, int groups,
+                                                       float eps, int apply_silu, __half* __restrict__ out, int ppb) {
+  extern __shared__ float s_ab[];  // a[c], b[c]
+  float* s_a = s_ab;
+  float* s_b = s_ab + c;
+  const int n = blockIdx.y;
+  const int cpg = c / groups;
+  const double cnt = static_cast<double>(cpg) * hw;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const int g = ch / cpg;
+    const double sum = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 0];
+    const double sq = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 1];
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float a = rstd * gamma[ch];
+    s_a[ch] = a;
+    s_b[ch] = beta[ch] - static_cast<float>(mean) * a;
+  }
+  __syncthreads();
+  const int vpp = c >> 3;  // 16-byte vectors per pixel
+  const int p0 = blockIdx.x * ppb;
+  const int npix = min(ppb, hw - p0);
+  const int total = npix * vpp;
+  const uint4* xin = reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(n) * hw + p0) * c);
+  uint4* yout = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(n) * hw + p0) * c);
+  for (int v = threadIdx.x; v < total; v += blockDim.x) {
+    const int cv = (v % vpp) << 3;
+    uint4 u = __ldg(xin + v);
+    __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(h2[e]);
+      f.x = fmaf(f.x, s_a[cv + 2 * e], s_b[cv + 2 * e]);
+      f.y = fmaf(f.y, s_a[cv + 2 * e + 1], s_b[cv + 2 * e + 1]);
+      if (apply_silu) {
+        f.x = __fdividef(f.x, 1.f + __expf(-f.x));
+        f.y = __fdividef(f.y, 1.f + __expf(-f.y));
+      }
+      h2[e] = __floats2half2_rn(f.x, f.y);
+    }
+    yout[v] = u;
+  }
+}
+
+// probs[r, :] = softmax(scale * scores[r, :]); one block per row, row staged in shared memory.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ scores, int cols, float scale,
+                                                           __half* __restrict__ probs) {
+  extern __shared__ float s_row[];
+  __shared__ float s_red[8];
+  const int64_t r = blockIdx.x;
+  const float* src = scores + r * cols;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    const float v = src[i] * scale;
+    s_row[i] = v;
+    m = fmaxf(m, v);
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = s_red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) m = fmaxf(m, s_red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    const float e = __expf(s_row[i] - m);
+    s_row[i] = e;
+    sum += e;
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += s_red[i];
+  const float inv = 1.f / sum;
+  __half* dst = probs + r * cols;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) dst[i] = __float2half_rn(s_row[i] * inv);
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, int64_t n, __half* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+
+}  // namespace wfk
+
+extern "C" int wfk_groupnorm_apply(const void* x, const double* stats, const float* gamma, const float* beta, int n,
+                                   int hw, int c, int groups, float eps, int apply_silu, void* out, void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(x && stats && gamma && beta && out, "null pointer");
+  WFK_REQUIRE(n > 0 && hw > 0 && c > 0 && groups > 0, "empty problem");
+  WFK_REQUIRE(c % 8 == 0 && c % groups == 0 && c <= 4096, "unsupported channel count c=%d groups=%d", c, groups);
+  WFK_REQUIRE(n <= 65535, "n too large");
+  int ppb = 16384 / c;
+  if (ppb < 1) ppb = 1;
+  dim3 grid((hw + ppb - 1) / ppb, n);
+  wfk::gn_apply_kernel<<<grid, 256, 2 * c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), stats, gamma, beta, hw, c, groups, eps, apply_silu, static_cast<__half*>(out), ppb);
+  return wfk::launched("gn_apply_kernel");
+}
+
+extern "C" int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(scores && probs, "null pointer");
+  WFK_REQUIRE(rows > 0 && rows < (1ll << 31) && cols > 0 && cols <= 11264, "unsupported softmax shape");
+  wfk::softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, cols * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      scores, cols, scale, static_cast<__half*>(probs));
+  return wfk::launched("softmax_rows_kernel");
+}
+
+extern "C" int wfk_f32_to_f16(const float* in, int64_t n, void* out, void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(in && out && n > 0, "bad argument");
+  const int64_t blocks = (n + 255) / 256;
+  wfk::f32_to_f16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, n, static_cast<__half*>(out));
+  return wfk::launched("f32_to_f16_kernel");
+}

@@ -1,0 +1,80 @@
+// VIL frame staging: uint8 NHWT (SEVIR on-disk layout) -> normalised float N T (C=1) H W.
+// Replaces SEVIRDataLoader.preprocess_data_dict + change_layout (reference
+// pipeline/datasets/sevir/sevir.py:626-666, 88-101; cast at :587-592), bit-exactly:
+//   out = fl32(1/255) * ((float)u8 + 0)
+// HBM-bound: 128-bit loads of the byte stream into shared memory (the T=25 innermost bytes are
+// not 16-byte aligned per pixel, so the transpose happens in smem), 128-bit stores per frame plane.
+#include <cuda_fp16.h>
+
+#include "internal.h"
+
+namespace wfk {
+
+constexpr int kStagePix = 512;  // pixels per block
+
+template <bool HALF_OUT>
+__global__ void __launch_bounds__(256) stage_vil_kernel(const uint8_t* __restrict__ in, int hw, int t,
+                                                        void* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t s_bytes[];  // [kStagePix * t]
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * kStagePix;
+  const int npix = min(kStagePix, hw - p0);
+  const int nbytes = npix * t;
+  const uint8_t* src = in + (static_cast<int64_t>(n) * hw + p0) * t;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int nvec = nbytes >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(s_bytes);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) d4[i] = __ldg(s4 + i);
+    for (int i = (nvec << 4) + threadIdx.x; i < nbytes; i += blockDim.x) s_bytes[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < nbytes; i += blockDim.x) s_bytes[i] = src[i];
+  }
+  __syncthreads();
+  const float scale = 1.0f / 255.0f;  // == fl32(1/255) = 0x3b808081
+  // thread -> (frame index tq, group of 4 consecutive pixels pg)
+  const int groups = (npix + 3) >> 2;
+  for (int item = threadIdx.x; item < groups * t; item += blockDim.x) {
+    const int ti = item / groups, pg = (item - ti * groups) << 2;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = pg + j;
+      v[j] = (p < npix) ? __fmul_rn(static_cast<float>(s_bytes[p * t + ti]), scale) : 0.f;
+    }
+    const int64_t o = (static_cast<int64_t>(n) * t + ti) * hw + p0 + pg;
+    if (pg + 3 < npix && ((o & 3) == 0)) {
+      if (HALF_OUT) {
+        __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(static_cast<__half*>(out) + o) = u;
+      } else {
+        *reinterpret_cast<float4*>(static_cast<float*>(out) + o) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+      for (int j = 0; j < 4 && pg + j < npix; ++j) {
+        if (HALF_OUT) static_cast<__half*>(out)[o + j] = __float2half_rn(v[j]);
+        else static_cast<float*>(out)[o + j] = v[j];
+      }
+    }
+  }
+}
+
+}  // namespace wfk
+
+extern "C" int wfk_stage_vil_u8(const uint8_t* nhwt, int n, int h, int w, int t, void* out_ntchw, int out_dtype,
+                                void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(nhwt && out_ntchw, "null pointer");
+  WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && t > 0 && t <= 64, "unsupported shape n=%d h=%d w=%d t=%d", n, h, w, t);
+  WFK_REQUIRE(out_dtype == 0 || out_dtype == 1, "out_dtype must be 0 (f32) or 1 (f16)");
+  const int hw = h * w;
+  dim3 grid((hw + wfk::kStagePix - 1) / wfk::kStagePix, n);
+  const size_t smem = static_cast<size_t>(wfk::kStagePix) * t;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_dtype == 1) wfk::stage_vil_kernel<true><<<grid, 256, smem, s>>>(nhwt, hw, t, out_ntchw);
+  else wfk::stage_vil_kernel<false><<<grid, 256, smem, s>>>(nhwt, hw, t, out_ntchw);
+  return wfk::launched("stage_vil_kernel");
+}

@@ -1,0 +1,534 @@
+"""Host-side executor of the Path-B autoencoder on libwfk_b200.so.
+
+PyTorch is used for device memory and streams only; every arithmetic op below is one of the
+hand-written sm_100a kernels reached through the C ABI (``_cabi``). Activations are NHWC fp16 on
+device; weights are packed once (fp16, ``[slab][cout][cin]``) from a reference ``state_dict``.
+
+The layer sequence follows the reference modules (paths relative to the reference repo):
+``Encoder.forward`` (pipeline/models/autoencoderkl/vae.py:70-86), ``Decoder.forward``
+(vae.py:150-166), ``ResnetBlock2D.forward`` (resnet.py:454-495), ``Downsample2D`` /
+``Upsample2D`` (resnet.py:181-190, 108-143), ``AttentionBlock.forward`` (attention.py:136-189),
+``AutoencoderKL.encode/_decode`` (autoencoder_kl.py:80-89).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import ConvDesc, Tap
+
+F16 = torch.float16
+GN_EPS = 1e-6  # resnet_eps passed by Encoder/Decoder (vae.py:41,57,128)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _Pool:
+    """Free-list of device buffers keyed by (numel, dtype): plans bind raw pointers, so buffers
+    are handed out at plan-build time following the static liveness of the layer sequence."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free: Dict[Tuple[int, torch.dtype], List[torch.Tensor]] = {}
+        self.all: List[torch.Tensor] = []
+
+    def get(self, shape: Sequence[int], dtype=F16) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        lst = self.free.get((n, dtype))
+        if lst:
+            return lst.pop().view(*shape)
+        t = torch.empty(n, dtype=dtype, device=self.device)
+        self.all.append(t)
+        return t.view(*shape)
+
+    def put(self, t: torch.Tensor) -> None:
+        self.free.setdefault((t.numel(), t.dtype), []).append(t.reshape(-1))
+
+
+class _Act:
+    """An NHWC fp16 activation plus the GroupNorm statistics its producer accumulated."""
+
+    def __init__(self, t: torch.Tensor, stats: Optional[torch.Tensor]):
+        self.t = t          # [N, H, W, C]
+        self.stats = stats  # [N, 32, 2] float64 or None
+
+    @property
+    def shape(self):
+        return self.t.shape
+
+
+class PackedAKL:
+    """fp16 / fp32 device copies of the AutoencoderKL weights in kernel layouts."""
+
+    def __init__(self, cfg: dict, sd: Dict[str, torch.Tensor], device):
+        self.cfg = dict(cfg)
+        self.device = device
+        self.t: Dict[str, torch.Tensor] = {}
+        boc = list(cfg["block_out_channels"])
+        self.groups = int(cfg.get("norm_num_groups", 32))
+        for name, w in sd.items():
+            w = w.detach().to(device=device, dtype=torch.float32)
+            if name.endswith(".weight") and w.ndim == 4 and w.shape[2] == 3:
+                mod = name[: -len(".weight")]
+                cout, cin = w.shape[0], w.shape[1]
+                if mod == "encoder.conv_in" or mod == "decoder.conv_in":
+                    # direct kernel: [cin*9][cout] fp32
+                    self.t[mod + ".w_direct"] = w.permute(1, 2, 3, 0).reshape(cin * 9, cout).contiguous()
+                elif mod == "encoder.conv_out" or mod == "decoder.conv_out":
+                    # direct kernel: [cout][9][cin] fp16
+                    self.t[mod + ".w_direct"] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin).contiguous().to(F16)
+                elif ".upsamplers." in mod:
+                    self.t[mod + ".w_phase"] = self._phase_weights(w)
+                else:
+                    # [9][cout][cin] fp16, slab = r*3+s
+                    self.t[mod + ".w"] = w.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().to(F16)
+            elif name.endswith(".weight") and w.ndim == 4 and w.shape[2] == 1:
+                mod = name[: -len(".weight")]
+                if mod in ("quant_conv", "post_quant_conv"):
+                    self.t[mod + ".w"] = w.reshape(w.shape[0], w.shape[1]).contiguous()
+                else:  # conv_shortcut
+                    self.t[mod + ".w"] = w.reshape(1, w.shape[0], w.shape[1]).contiguous().to(F16)
+            elif name.endswith(".weight") and w.ndim == 2:  # attention linears
+                self.t[name[: -len(".weight")] + ".w"] = w.contiguous().to(F16)
+            else:
+                self.t[name] = w.contiguous()
+        # fused parameters
+        for p in ("encoder.mid_block.attentions.0", "decoder.mid_block.attentions.0"):
+            if p + ".query.w" in self.t:
+                self.t[p + ".qk.w"] = torch.cat([self.t[p + ".query.w"], self.t[p + ".key.w"]], 0).unsqueeze(0).contiguous()
+                self.t[p + ".qk.bias"] = torch.cat([self.t[p + ".query.bias"], self.t[p + ".key.bias"]], 0).contiguous()
+                self.t[p + ".proj_attn.w3"] = self.t[p + ".proj_attn.w"].unsqueeze(0).contiguous()
+        for k in list(self.t):
+            if k.endswith(".conv_shortcut.w"):
+                r = k[: -len(".conv_shortcut.w")]
+                self.t[r + ".conv2.bias_sc"] = (self.t[r + ".conv2.bias"] + self.t[r + ".conv_shortcut.bias"]).contiguous()
+
+    @staticmethod
+    def _phase_weights(w: torch.Tensor) -> torch.Tensor:
+        """nearest-x2 upsample + conv3x3 == four 2x2 convolutions on the low-res input, one per
+        output parity (a, b): rows {2y+a-1, 2y+a, 2y+a+1} // 2 collapse onto two source rows, so the
+        3x3 weights are pre-summed. Returns [16 slabs = (a,b,i,j)][cout][cin] fp16."""
+        cout, cin = w.shape[0], w.shape[1]
+        sets = {0: [[0], [1, 2]], 1: [[0, 1], [2]]}
+        out = torch.zeros(2, 2, 2, 2, cout, cin, dtype=torch.float32, device=w.device)
+        for a in (0, 1):
+            for b in (0, 1):
+                for i, rs in enumerate(sets[a]):
+                    for j, ss in enumerate(sets[b]):
+                        acc = torch.zeros(cout, cin, dtype=torch.float32, device=w.device)
+                        for r in rs:
+                            for s in ss:
+                                acc = acc + w[:, :, r, s]
+                        out[a, b, i, j] = acc
+        return out.reshape(16, cout, cin).contiguous().to(F16)
+
+
+# rows touched by upsample phase a: a=0 -> (y-1, y); a=1 -> (y, y+1)
+_PHASE_OFFS = {0: (-1, 0), 1: (0, 1)}
+
+
+class AKLEngine:
+    """Builds (once per input shape) and runs the kernel sequence of encode / decode."""
+
+    def __init__(self, cfg: dict, sd: Dict[str, torch.Tensor], device="cuda:0", operand_bf16: bool = False):
+        self.device = torch.device(device)
+        dev_index = self.device.index if self.device.index is not None else 0
+        self.lib = _cabi.init(dev_index)
+        if operand_bf16:
+            raise NotImplementedError("bf16 operands fail the 1e-2 relative-L2 parity gate; fp16 only (DESIGN.md)")
+        self.cfg = dict(cfg)
+        self.boc = list(cfg["block_out_channels"])
+        self.lpb = int(cfg.get("layers_per_block", 1))
+        self.lc = int(cfg.get("latent_channels", 4))
+        self.groups = int(cfg.get("norm_num_groups", 32))
+        self.in_ch = int(cfg.get("in_channels", 3))
+        self.out_ch = int(cfg.get("out_channels", 3))
+        for c in self.boc:
+            if c % 64 != 0 or (c // self.groups) not in (4, 8, 16):
+                raise ValueError(f"block_out_channels={self.boc} unsupported: channels must be multiples of 64 with "
+                                 f"4, 8 or 16 channels per GroupNorm group")
+        if self.in_ch > 4 or self.lc > 4 or self.out_ch not in (1, 2, 4, 8) or 2 * self.lc not in (2, 4, 8):
+            raise ValueError("unsupported in/out/latent channel counts for the direct edge-conv kernels")
+        self.w = PackedAKL(cfg, sd, self.device)
+        self._plans: Dict[Tuple, "_Program"] = {}
+        self._keep: List = []
+
+    # ------------------------------------------------------------------ public
+    def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
+        """x [N, in_ch, H, W] fp32 cuda -> moments [N, 2*lc, H/8, W/8] fp32."""
+        prog = self._program("enc", tuple(x.shape))
+        return prog.run(x)
+
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        """z [N, lc, h, w] fp32 cuda -> [N, out_ch, 8h, 8w] fp32."""
+        prog = self._program("dec", tuple(z.shape))
+        return prog.run(z)
+
+    def _program(self, kind: str, shape: Tuple[int, ...]) -> "_Program":
+        key = (kind, shape)
+        prog = self._plans.get(key)
+        if prog is None:
+            prog = _Program(self, kind, shape)
+            self._plans[key] = prog
+        return prog
+
+
+class _Program:
+    """A static list of (C function, args) bound to preallocated buffers for one input shape."""
+
+    def __init__(self, eng: AKLEngine, kind: str, shape: Tuple[int, ...]):
+        self.eng = eng
+        self.lib = eng.lib
+        self.dev = eng.device
+        self.pool = _Pool(self.dev)
+        self.ops: List[Tuple[Callable, tuple, str]] = []
+        self.plans: List[int] = []
+        self.keep: List = []
+        self.stats_bufs: List[torch.Tensor] = []
+        self.n = int(shape[0])
+        n_stats = 80
+        self.stats_arena = torch.zeros(n_stats, self.n, eng.groups, 2, dtype=torch.float64, device=self.dev)
+        self._stats_used = 0
+        self.input = torch.empty(shape, dtype=torch.float32, device=self.dev)
+        if kind == "enc":
+            self.output = self._build_encoder(shape)
+        else:
+            self.output = self._build_decoder(shape)
+
+    def __del__(self):
+        try:
+            for p in self.plans:
+                self.lib.wfk_conv_plan_destroy(p)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ running
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise TypeError("expected a float32 CUDA tensor")
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        self.input.copy_(x)
+        self.stats_arena.zero_()
+        for fn, args, what in self.ops:
+            _cabi.check(fn(*args, stream), what)
+        return self.output.clone()
+
+    # ------------------------------------------------------------------ helpers
+    def _new_stats(self) -> torch.Tensor:
+        s = self.stats_arena[self._stats_used]
+        self._stats_used += 1
+        if self._stats_used > self.stats_arena.shape[0]:
+            raise RuntimeError("stats arena exhausted")
+        return s
+
+    def _add(self, fn, args, what):
+        self.ops.append((fn, tuple(args), what))
+
+    def _conv_plan(self, desc: ConvDesc, what: str):
+        h = C.c_void_p()
+        _cabi.check(self.lib.wfk_conv_plan_create(C.byref(desc), C.byref(h)), f"conv_plan_create[{what}]")
+        self.plans.append(h)
+        self._add(self.lib.wfk_conv_plan_run, (h,), what)
+
+    @staticmethod
+    def _view_nhwc(desc_view, t: torch.Tensor, n, h, w, c, pitch_c=None):
+        pitch = c if pitch_c is None else pitch_c
+        desc_view.ptr = t.data_ptr()
+        dims = (c, w, 1, h, n)
+        strides = (2, pitch * 2, w * pitch * 2, w * pitch * 2, h * w * pitch * 2)
+        for i in range(5):
+            desc_view.dim[i] = dims[i]
+            desc_view.stride[i] = strides[i]
+
+    @staticmethod
+    def _view_w(desc_view, t: torch.Tensor, k, nrows, slabs, pitch_k=None, slab_stride=None):
+        pitch = k if pitch_k is None else pitch_k
+        desc_view.ptr = t.data_ptr()
+        dims = (k, nrows, slabs)
+        strides = (2, pitch * 2, (nrows * pitch * 2) if slab_stride is None else slab_stride)
+        for i in range(3):
+            desc_view.dim[i] = dims[i]
+            desc_view.stride[i] = strides[i]
+
+    def _epilogue(self, d: ConvDesc, bias, residual, out_h, out_f, stats, out_rows, out_cols, ldc, sy=1, sx=1):
+        d.bias = _ptr(bias)
+        d.residual = _ptr(residual)
+        d.out_h = _ptr(out_h)
+        d.out_f = _ptr(out_f)
+        d.stats = _ptr(stats)
+        d.out_rows, d.out_cols, d.out_sy, d.out_sx, d.ldc = out_rows, out_cols, sy, sx, ldc
+        d.cpg = (d.n_total // self.eng.groups) if stats is not None else 0
+        d.operand_bf16 = 0
+
+    # ------------------------------------------------------------------ layer builders
+    def conv3x3(self, x: _Act, wname: str, bias: torch.Tensor, cout: int, residual: Optional[torch.Tensor] = None,
+                shortcut: Optional[Tuple[torch.Tensor, str]] = None, want_stats=True, what="conv3x3") -> _Act:
+        """3x3 stride-1 pad-1 conv (+bias, +residual | fused 1x1 shortcut) -> new activation."""
+        n, h, w, cin = x.shape
+        wt = self.eng.w.t[wname]
+        out = self.pool.get((n, h, w, cout))
+        stats = self._new_stats() if want_stats else None
+        d = ConvDesc()
+        self._view_nhwc(d.a[0], x.t, n, h, w, cin)
+        self._view_w(d.b[0], wt, cin, cout, 9)
+        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, h, w, cout
+        d.num_phases, d.taps_per_phase = 1, 9
+        k = 0
+        for r in range(3):
+            for s in range(3):
+                d.taps[k] = Tap(s - 1, r - 1, 0, 0, 0, r * 3 + s, cin // 64, 0)
+                k += 1
+        if shortcut is not None:
+            xs, sname = shortcut
+            cs = xs.shape[3]
+            self._view_nhwc(d.a[1], xs, n, h, w, cs)
+            self._view_w(d.b[1], self.eng.w.t[sname], cs, cout, 1)
+            d.taps[9] = Tap(0, 0, 0, 1, 0, 0, cs // 64, 0)
+            d.taps_per_phase = 10
+        d.a_frame_mul, d.b_frame_mul = 1, 0
+        self._epilogue(d, bias, residual, out, None, stats, h, w, cout)
+        self._conv_plan(d, what)
+        return _Act(out, stats)
+
+    def downsample(self, x: _Act, wname: str, bias: torch.Tensor, what="downsample") -> _Act:
+        """F.pad(0,1,0,1) + conv3x3 stride 2 pad 0 (resnet.py:183-188) through a parity view of the input:
+        dims (2C, W/2, 2, H/2, N) so that input pixel (2y+r, 2x+s) is (c + (s%2)C, x + s//2, r%2, y + r//2)."""
+        n, h, w, c = x.shape
+        if h % 2 or w % 2:
+            raise ValueError("downsample needs even H and W")
+        wt = self.eng.w.t[wname]
+        oh, ow = h // 2, w // 2
+        out = self.pool.get((n, oh, ow, c))
+        stats = self._new_stats()
+        d = ConvDesc()
+        v = d.a[0]
+        v.ptr = x.t.data_ptr()
+        dims = (2 * c, ow, 2, oh, n)
+        strides = (2, 2 * c * 2, w * c * 2, 2 * w * c * 2, h * w * c * 2)
+        for i in range(5):
+            v.dim[i] = dims[i]
+            v.stride[i] = strides[i]
+        self._view_w(d.b[0], wt, c, c, 9)
+        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, oh, ow, c
+        d.num_phases, d.taps_per_phase = 1, 9
+        k = 0
+        for r in range(3):
+            for s in range(3):
+                d.taps[k] = Tap(s // 2, r // 2, r % 2, 0, (s % 2) * c, r * 3 + s, c // 64, 0)
+                k += 1
+        d.a_frame_mul, d.b_frame_mul = 1, 0
+        self._epilogue(d, bias, None, out, None, stats, oh, ow, c)
+        self._conv_plan(d, what)
+        return _Act(out, stats)
+
+    def upsample(self, x: _Act, wname: str, bias: torch.Tensor, what="upsample") -> _Act:
+        """F.interpolate(x2, nearest) + conv3x3 (resnet.py:128,137-139) as four 2x2 sub-pixel convolutions
+        on the low-res input (2.25x fewer MACs, no upsampled tensor materialised)."""
+        n, h, w, c = x.shape
+        wt = self.eng.w.t[wname]  # [16][c][c]
+        out = self.pool.get((n, 2 * h, 2 * w, c))
+        stats = self._new_stats()
+        d = ConvDesc()
+        self._view_nhwc(d.a[0], x.t, n, h, w, c)
+        self._view_w(d.b[0], wt, c, c, 16)
+        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, h, w, c
+        d.num_phases, d.taps_per_phase = 4, 4
+        for a in (0, 1):
+            for b in (0, 1):
+                ph = a * 2 + b
+                for i in (0, 1):
+                    for j in (0, 1):
+                        d.taps[ph * 4 + i * 2 + j] = Tap(_PHASE_OFFS[b][j], _PHASE_OFFS[a][i], 0, 0, 0,
+                                                         ph * 4 + i * 2 + j, c // 64, 0)
+        d.a_frame_mul, d.b_frame_mul = 1, 0
+        self._epilogue(d, bias, None, out, None, stats, 2 * h, 2 * w, c, sy=2, sx=2)
+        self._conv_plan(d, what)
+        return _Act(out, stats)
+
+    def gn(self, x: _Act, pname: str, silu=True, what="groupnorm") -> torch.Tensor:
+        n, h, w, c = x.shape
+        out = self.pool.get((n, h, w, c))
+        t = self.eng.w.t
+        self._add(self.lib.wfk_groupnorm_apply,
+                  (x.t.data_ptr(), x.stats.data_ptr(), t[pname + ".weight"].data_ptr(), t[pname + ".bias"].data_ptr(),
+                   n, h * w, c, self.eng.groups, GN_EPS, 1 if silu else 0, out.data_ptr()), what)
+        return out
+
+    def resnet(self, x: _Act, p: str) -> _Act:
+        """ResnetBlock2D.forward (resnet.py:454-495)."""
+        t = self.eng.w.t
+        cin = x.shape[3]
+        cout = t[p + ".conv1.bias"].numel()
+        a1 = self.gn(x, p + ".norm1", what=p + ".norm1")
+        h1 = self.conv3x3(_Act(a1, None), p + ".conv1.w", t[p + ".conv1.bias"], cout, what=p + ".conv1")
+        self.pool.put(a1)
+        a2 = self.gn(h1, p + ".norm2", what=p + ".norm2")
+        self.pool.put(h1.t)
+        if (p + ".conv_shortcut.w") in t:
+            out = self.conv3x3(_Act(a2, None), p + ".conv2.w", t[p + ".conv2.bias_sc"], cout,
+                               shortcut=(x.t, p + ".conv_shortcut.w"), what=p + ".conv2+shortcut")
+        else:
+            out = self.conv3x3(_Act(a2, None), p + ".conv2.w", t[p + ".conv2.bias"], cout, residual=x.t,
+                               what=p + ".conv2+res")
+        self.pool.put(a2)
+        self.pool.put(x.t)
+        return out
+
+    def attention(self, x: _Act, p: str) -> _Act:
+        """AttentionBlock.forward, one head (attention.py:136-189)."""
+        t = self.eng.w.t
+        n, h, w, c = x.shape
+        T = h * w
+        if T % 8:
+            raise ValueError("attention needs h*w to be a multiple of 8")
+        a = self.gn(x, p + ".group_norm", silu=False, what=p + ".group_norm")
+        # q | k projection: [n, T, 2c]
+        qk = self.pool.get((n, T, 2 * c))
+        d = ConvDesc()
+        self._view_nhwc(d.a[0], a, n, 1, T, c)
+        self._view_w(d.b[0], t[p + ".qk.w"], c, 2 * c, 1)
+        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, 1, T, 2 * c
+        d.num_phases, d.taps_per_phase = 1, 1
+        d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
+        d.a_frame_mul, d.b_frame_mul = 1, 0
+        self._epilogue(d, t[p + ".qk.bias"], None, qk, None, None, 1, T, 2 * c)
+        self._conv_plan(d, p + ".qk")
+        # V^T = Wv . X^T : [n, c, T]   (value bias is added after P.V: softmax rows sum to 1)
+        vt = self.pool.get((n, c, T))
+        d = ConvDesc()
+        self._view_nhwc(d.a[0], t[p + ".value.w"], 1, 1, c, c)
+        self._view_w(d.b[0], a, c, T, n)
+        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, 1, c, T
+        d.num_phases, d.taps_per_phase = 1, 1
+        d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
+        d.a_frame_mul, d.b_frame_mul = 0, 1
+        self._epilogue(d, None, None, vt, None, None, 1, c, T)
+        self._conv_plan(d, p + ".value^T")
+        self.pool.put(a)
+        # scores = Q K^T (fp32), scale folded into the softmax
+        scores = self.pool.get((n, T, T), torch.float32)
+        d = ConvDesc()
+        self._view_nhwc(d.a[0], qk, n, 1, T, c, pitch_c=2 * c)
+        kview = qk.view(-1)[c:]
+        self._view_w(d.b[0], kview, c, T, n, pitch_k=2 * c, slab_stride=T * 2 * c * 2)
+        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, 1, T, T
+        d.num_phases, d.taps_per_phase = 1, 1
+        d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
+        d.a_frame_mul, d.b_frame_mul = 1, 1
+        self._epilogue(d, None, None, None, scores, None, 1, T, T)
+        self._conv_plan(d, p + ".scores")
+        probs = self.pool.get((n, T, T))
+        self._add(self.lib.wfk_softmax_rows,
+                  (scores.data_ptr(), n * T, T, 1.0 / math.sqrt(c), probs.data_ptr()), p + ".softmax")
+        self.pool.put(qk)
+        # O = P V (+ value bias)
+        o = self.pool.get((n, T, c))
+        d = ConvDesc()
+        self._view_nhwc(d.a[0], probs, n, 1, T, T)
+        self._view_w(d.b[0], vt, T, c, n)
+        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, 1, T, c
+        d.num_phases, d.taps_per_phase = 1, 1
+        d.taps[0] = Tap(0, 0, 0, 0, 0, 0, (T + 63) // 64, 0)
+        d.a_frame_mul, d.b_frame_mul = 1, 1
+        self._epilogue(d, t[p + ".value.bias"], None, o, None, None, 1, T, c)
+        self._conv_plan(d, p + ".pv")
+        self.pool.put(scores)
+        self.pool.put(probs)
+        self.pool.put(vt)
+        # proj + residual
+        out = self.pool.get((n, h, w, c))
+        stats = self._new_stats()
+        d = ConvDesc()
+        self._view_nhwc(d.a[0], o, n, 1, T, c)
+        self._view_w(d.b[0], t[p + ".proj_attn.w3"], c, c, 1)
+        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, 1, T, c
+        d.num_phases, d.taps_per_phase = 1, 1
+        d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
+        d.a_frame_mul, d.b_frame_mul = 1, 0
+        self._epilogue(d, t[p + ".proj_attn.bias"], x.t, out, None, stats, 1, T, c)
+        self._conv_plan(d, p + ".proj+res")
+        self.pool.put(o)
+        self.pool.put(x.t)
+        return _Act(out, stats)
+
+    def mid(self, x: _Act, p: str) -> _Act:
+        x = self.resnet(x, p + ".resnets.0")
+        x = self.attention(x, p + ".attentions.0")
+        return self.resnet(x, p + ".resnets.1")
+
+    # ------------------------------------------------------------------ networks
+    def _build_encoder(self, shape) -> torch.Tensor:
+        eng, t = self.eng, self.eng.w.t
+        n, cin, H, W = shape
+        nb = len(eng.boc)
+        if cin != eng.in_ch or H % (1 << (nb - 1)) or W % (1 << (nb - 1)):
+            raise ValueError(f"encode: bad input shape {shape}")
+        c0 = eng.boc[0]
+        s0 = self.pool.get((n, H, W, c0))
+        st = self._new_stats()
+        self._add(self.lib.wfk_conv3x3_small_cin,
+                  (self.input.data_ptr(), n, cin, H, W, None, None, t["encoder.conv_in.w_direct"].data_ptr(),
+                   t["encoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
+                  "encoder.conv_in")
+        x = _Act(s0, st)
+        for i in range(nb):
+            for j in range(eng.lpb):
+                x = self.resnet(x, f"encoder.down_blocks.{i}.resnets.{j}")
+            if i != nb - 1:
+                p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+                y = self.downsample(x, p + ".w", t[p + ".bias"], what=p)
+                self.pool.put(x.t)
+                x = y
+        x = self.mid(x, "encoder.mid_block")
+        a = self.gn(x, "encoder.conv_norm_out", what="encoder.conv_norm_out")
+        self.pool.put(x.t)
+        _, h, w, c = x.shape
+        out = torch.empty((n, 2 * eng.lc, h, w), dtype=torch.float32, device=self.dev)
+        self._add(self.lib.wfk_conv3x3_small_cout,
+                  (a.data_ptr(), n, h, w, c, t["encoder.conv_out.w_direct"].data_ptr(),
+                   t["encoder.conv_out.bias"].data_ptr(), 2 * eng.lc, t["quant_conv.w"].data_ptr(),
+                   t["quant_conv.bias"].data_ptr(), out.data_ptr()), "encoder.conv_out+quant_conv")
+        return out
+
+    def _build_decoder(self, shape) -> torch.Tensor:
+        eng, t = self.eng, self.eng.w.t
+        n, lc, h, w = shape
+        nb = len(eng.boc)
+        if lc != eng.lc:
+            raise ValueError(f"decode: bad latent shape {shape}")
+        rev = list(reversed(eng.boc))
+        c0 = rev[0]
+        s0 = self.pool.get((n, h, w, c0))
+        st = self._new_stats()
+        self._add(self.lib.wfk_conv3x3_small_cin,
+                  (self.input.data_ptr(), n, lc, h, w, t["post_quant_conv.w"].data_ptr(),
+                   t["post_quant_conv.bias"].data_ptr(), t["decoder.conv_in.w_direct"].data_ptr(),
+                   t["decoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
+                  "post_quant_conv+decoder.conv_in")
+        x = _Act(s0, st)
+        x = self.mid(x, "decoder.mid_block")
+        for i in range(nb):
+            for j in range(eng.lpb + 1):
+                x = self.resnet(x, f"decoder.up_blocks.{i}.resnets.{j}")
+            if i != nb - 1:
+                p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                y = self.upsample(x, p + ".w_phase", t[p + ".bias"], what=p)
+                self.pool.put(x.t)
+                x = y
+        a = self.gn(x, "decoder.conv_norm_out", what="decoder.conv_norm_out")
+        self.pool.put(x.t)
+        _, H, W, c = x.shape
+        out = torch.empty((n, eng.out_ch, H, W), dtype=torch.float32, device=self.dev)
+        self._add(self.lib.wfk_conv3x3_small_cout,
+                  (a.data_ptr(), n, H, W, c, t["decoder.conv_out.w_direct"].data_ptr(),
+                   t["decoder.conv_out.bias"].data_ptr(), eng.out_ch, None, None, out.data_ptr()),
+                  "decoder.conv_out")
+        return out
