@@ -84,12 +84,14 @@ typedef struct wfk_metric_partials {
 } wfk_metric_partials;
 
 size_t wfk_metrics_workspace_bytes(int frames, int h, int w);
-/* pred, tgt: [frames, h, w] fp32 (any values; clamped inside). thresholds: HOST array of fp32
- * values (already rounded the way torch rounds the Python-float threshold, SURVEY hazard H2).
- * out: DEVICE struct, fully overwritten. workspace: DEVICE scratch of workspace_bytes. */
+/* pred, tgt: [frames, h, w] fp32. clamp01 != 0 applies calc_metrics' clamp(0,1) (metrics.py:92-93)
+ * on load; 0 scores the values as given (the stand-alone csi/hss/ssim/psnr/crps functions).
+ * thresholds: HOST array of fp32 values (already rounded the way torch rounds the Python-float
+ * threshold, SURVEY hazard H2). out: DEVICE struct, fully overwritten. workspace: DEVICE scratch
+ * of wfk_metrics_workspace_bytes. */
 int wfk_metrics(const float* pred, const float* tgt, int frames, int h, int w, const float* thresholds,
-                int n_thresholds, wfk_metric_partials* out, void* workspace, size_t workspace_bytes,
-                void* stream);
+                int n_thresholds, int clamp01, wfk_metric_partials* out, void* workspace,
+                size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a3-a6, a9  Autoencoder building blocks (activations NHWC fp16 on device).

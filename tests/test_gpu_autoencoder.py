@@ -1,0 +1,246 @@
+"""-m gpu: the tcgen05 implicit-GEMM convolution and the whole AutoencoderKL drop-in against the fp32
+oracle / reference goldens. Tolerance for forecasts: 1e-2 relative L2 (north_star); fp16 tensor-core
+operands with fp32 accumulation land at ~2-3e-3."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def engine(akl_weights):
+    from weatherforecastingtoolkit_b200.engine import AKLEngine
+    cfg, sd = akl_weights
+    return AKLEngine(cfg, sd, device=DEV)
+
+
+@pytest.fixture(scope="module")
+def model(akl_weights):
+    from weatherforecastingtoolkit_b200.models.autoencoderkl import AutoencoderKL
+    cfg, sd = akl_weights
+    m = AutoencoderKL(**cfg)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV)
+
+
+class _Harness:
+    """Builds and runs single layers of engine._Program."""
+
+    def __new__(cls, eng, n):
+        from weatherforecastingtoolkit_b200.engine import _Pool, _Program
+        self = object.__new__(_Program)
+        self.eng, self.lib, self.dev = eng, eng.lib, eng.device
+        self.pool = _Pool(self.dev)
+        self.ops, self.plans, self.keep = [], [], []
+        self.n = n
+        self.stats_arena = torch.zeros(8, n, eng.groups, 2, dtype=torch.float64, device=self.dev)
+        self._stats_used = 0
+        return self
+
+
+def _go(h):
+    from weatherforecastingtoolkit_b200 import _cabi
+    stream = torch.cuda.current_stream().cuda_stream
+    h.stats_arena.zero_()
+    for fn, args, what in h.ops:
+        _cabi.check(fn(*args, stream), what)
+    torch.cuda.synchronize()
+
+
+def _ref_stats(y, groups):
+    n, h, w, c = y.shape
+    g = y.double().reshape(n, h * w, groups, c // groups)
+    return torch.stack([g.sum(dim=(1, 3)), (g * g).sum(dim=(1, 3))], dim=-1)
+
+
+CONV_CASES = [
+    ("plain", 2, 16, 16, 128, 128), ("plain", 1, 48, 48, 128, 256), ("plain", 1, 10, 30, 512, 512),
+    ("residual", 2, 24, 40, 256, 512), ("shortcut", 1, 32, 32, 128, 256), ("shortcut", 2, 8, 8, 512, 256),
+    ("down", 2, 32, 48, 128, 128), ("down", 1, 6, 6, 512, 512), ("up", 1, 24, 24, 256, 256),
+    ("up", 2, 5, 7, 512, 512), ("residual", 2, 96, 96, 512, 512), ("plain", 1, 384, 384, 128, 128),
+]
+
+
+@pytest.mark.parametrize("mode,n,h,w,cin,cout", CONV_CASES)
+def test_conv_gemm(engine, mode, n, h, w, cin, cout):
+    """Reference op: F.conv2d in fp32 on the same fp16-rounded operands (the tensor-core path multiplies
+    fp16 and accumulates fp32; only the fp16 store of the result differs: <= 2^-11 relative)."""
+    from weatherforecastingtoolkit_b200.engine import PackedAKL, _Act
+    torch.manual_seed(h * 1000 + cin + cout)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = torch.randn(n, h, w, cin, device=DEV).half()
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(9 * cin)
+    bias = torch.randn(cout, device=DEV)
+    xr = x.float().permute(0, 3, 1, 2)
+    hs = _Harness(engine, n)
+    t = engine.w.t
+    t["tmp.w"] = wt.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().half()
+    if mode in ("plain", "residual"):
+        res = torch.randn(n, h, w, cout, device=DEV).half() if mode == "residual" else None
+        out = hs.conv3x3(_Act(x, None), "tmp.w", bias, cout, residual=res)
+        ref = F.conv2d(xr, wt.half().float(), bias, padding=1).permute(0, 2, 3, 1)
+        if res is not None:
+            ref = ref + res.float()
+    elif mode == "shortcut":
+        cs = 2 * cin if cin <= 256 else cin // 2
+        xs = torch.randn(n, h, w, cs, device=DEV).half()
+        ws = torch.randn(cout, cs, 1, 1, device=DEV) / math.sqrt(cs)
+        t["tmp.sc"] = ws.reshape(1, cout, cs).contiguous().half()
+        out = hs.conv3x3(_Act(x, None), "tmp.w", bias, cout, shortcut=(xs, "tmp.sc"))
+        ref = (F.conv2d(xr, wt.half().float(), bias, padding=1)
+               + F.conv2d(xs.float().permute(0, 3, 1, 2), ws.half().float())).permute(0, 2, 3, 1)
+    elif mode == "down":
+        out = hs.downsample(_Act(x, None), "tmp.w", bias)
+        ref = F.conv2d(F.pad(xr, (0, 1, 0, 1)), wt.half().float(), bias, stride=2).permute(0, 2, 3, 1)
+    else:
+        t["tmp.w"] = PackedAKL._phase_weights(wt)
+        out = hs.upsample(_Act(x, None), "tmp.w", bias)
+        ref = F.conv2d(F.interpolate(xr, scale_factor=2.0, mode="nearest"), wt, bias, padding=1).permute(0, 2, 3, 1)
+    _go(hs)
+    assert out.t.shape == ref.shape
+    assert rel_l2(out.t.float(), ref) < (6e-4 if mode == "up" else 4e-4)
+    assert rel_l2(out.stats, _ref_stats(ref, engine.groups)) < 1e-4
+
+
+def test_groupnorm_silu(engine):
+    from weatherforecastingtoolkit_b200.engine import _Act
+    torch.manual_seed(0)
+    n, h, w, c = 2, 20, 12, 256
+    x = (torch.randn(n, h, w, c, device=DEV) * 2 + 0.5).half()
+    gamma, beta = torch.randn(c, device=DEV), torch.randn(c, device=DEV)
+    engine.w.t["tmpn.weight"], engine.w.t["tmpn.bias"] = gamma, beta
+    hs = _Harness(engine, n)
+    st = hs._new_stats()
+    for silu in (True, False):
+        hs.ops.clear()
+        out = hs.gn(_Act(x, st), "tmpn", silu=silu)
+        stream = torch.cuda.current_stream().cuda_stream
+        st.copy_(_ref_stats(x.float(), 32))
+        from weatherforecastingtoolkit_b200 import _cabi
+        for fn, args, what in hs.ops:
+            _cabi.check(fn(*args, stream), what)
+        torch.cuda.synchronize()
+        ref = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-6)
+        ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+        assert (out.float() - ref).abs().max().item() < 2e-2
+        assert rel_l2(out.float(), ref) < 5e-4
+
+
+@pytest.mark.parametrize("tag,hw,seed", [("akl64", 64, 11), ("akl384", 384, 12)])
+def test_akl_vs_reference_golden(model, golden_akl, tag, hw, seed):
+    """encode -> moments and decode(golden z) against outputs of the UNMODIFIED reference."""
+    from weatherforecastingtoolkit_b200.rollout import stage_vil
+    from weatherforecastingtoolkit_b200.synthetic import make_vil_sequences
+    n = golden_akl[f"{tag}_moments"].shape[0]
+    u8 = make_vil_sequences(n, hw, hw, 1, seed=seed)
+    x = stage_vil(u8.to(DEV))[:, 0]
+    post = model.encode(x)
+    want_m = torch.from_numpy(golden_akl[f"{tag}_moments"])
+    assert rel_l2(post.parameters, want_m) < 1e-2
+    assert rel_l2(post.mode(), want_m[:, :4]) < 1e-2
+    dec = model.decode(want_m[:, :4].contiguous().to(DEV))
+    assert dec.shape == (n, 1, hw, hw) and dec.dtype == torch.float32
+    assert rel_l2(dec, torch.from_numpy(golden_akl[f"{tag}_decoded"])) < 1e-2
+
+
+def test_akl_vs_oracle_odd_size(model, akl_weights):
+    """A size whose tiles are ragged everywhere (96x72 -> latent 12x9: 108 attention tokens... not a
+    multiple of 8 -> use 96x64: latent 12x8)."""
+    from oracle import akl_oracle as O
+    cfg, sd = akl_weights
+    torch.manual_seed(4)
+    x = torch.rand(3, 1, 96, 64)
+    with torch.no_grad():
+        m = O.akl_encode_moments(x, sd, cfg)
+        d = O.akl_decode(m[:, :4].contiguous(), sd, cfg)
+    assert rel_l2(model.encode(x.to(DEV)).parameters, m) < 1e-2
+    assert rel_l2(model.decode(m[:, :4].contiguous().to(DEV)), d) < 1e-2
+
+
+def test_drop_in_interface(model, akl_weights):
+    """The surface the reference train scripts use (autoencoder_kl.py:80-140, distributions.py:26-71)."""
+    cfg, sd = akl_weights
+    torch.manual_seed(0)
+    x = torch.rand(2, 1, 64, 64, device=DEV)
+    post = model.encode(x)
+    for attr in ("mean", "logvar", "std", "var", "parameters"):
+        assert hasattr(post, attr)
+    assert post.mode().shape == (2, 4, 8, 8)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    s1 = post.sample(generator=g)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    assert torch.equal(s1, post.sample(generator=g))
+    assert post.kl().shape == (2,) and post.nll(s1).shape == (2,)
+    dec, post2 = model(x, sample_posterior=False, return_posterior=True)
+    assert dec.shape == (2, 1, 64, 64)
+    model.enable_slicing()
+    sliced = model.decode(post.mode())
+    model.disable_slicing()
+    whole = model.decode(post.mode())
+    assert rel_l2(sliced, whole) < 1e-3
+    assert model.decoder.conv_out.weight.shape == (1, 128, 3, 3)
+    assert set(model.state_dict()) == set(sd)
+    with pytest.raises(RuntimeError):
+        model.encode(x.cpu())
+    from weatherforecastingtoolkit_b200.models.autoencoderkl import AutoencoderKL
+    with pytest.raises(ValueError):
+        AutoencoderKL(down_block_types=("AttnDownBlock2D",))
+
+
+def test_rollout_validation_step_vs_reference_golden(akl_weights, golden_akl, golden_metrics):
+    """Path-B validation_step (encode 25 -> Linear 52->48 -> decode 12+12 -> calc_metrics) at B=1, 64x64
+    against tensors produced by the unmodified reference modules."""
+    from oracle import metrics_oracle as MO
+    from weatherforecastingtoolkit_b200 import metrics as M
+    from weatherforecastingtoolkit_b200.rollout import PathBNowcast
+    from weatherforecastingtoolkit_b200.synthetic import make_predictor_params, make_vil_sequences
+    cfg, sd = akl_weights
+    net = PathBNowcast(cfg, posterior="mode", frames_per_call=16)
+    net.autoencoder.autoencoder.load_state_dict(sd, strict=True)
+    w, b = make_predictor_params(seed=0)
+    net.predictor.weight.data.copy_(w)
+    net.predictor.bias.data.copy_(b)
+    net = net.to(DEV)
+    u8 = make_vil_sequences(1, 64, 64, 25, seed=21).to(DEV)
+    dp, dt, loss = net.validation_step(u8)
+    assert dp.shape == (1, 12, 1, 64, 64)
+    assert rel_l2(dp, torch.from_numpy(golden_akl["rollout64_decoded_pred"])) < 1e-2
+    assert rel_l2(dt, torch.from_numpy(golden_akl["rollout64_decoded_tgt"])) < 1e-2
+    assert loss.item() == pytest.approx(float(golden_akl["rollout64_val_loss"]), rel=2e-2)
+    # float input path (the reference loader's output) gives the same result as the uint8 path
+    dp2, _, _ = net.validation_step((u8.float() * np.float32(1 / 255)))
+    assert rel_l2(dp2, dp) < 1e-6
+    # scoring: counts are bit-exact ON IDENTICAL FORECASTS (oracle counts of the GPU's own forecasts)
+    got = M.metric_partials(dp, dt)
+    assert got.counts.tolist() == MO.integer_counts(dp.cpu(), dt.cpu()).tolist()
+    res = M.scores_from_partials(got, extended=True)
+    ref = MO.calc_metrics(dp.cpu(), dt.cpu())
+    for k, v in ref.items():
+        assert res[k] == pytest.approx(v, abs=1e-3 if "SSIM" in k else 1e-5, rel=1e-5), k
+    # and the scores land near the reference's scores of ITS forecasts (forecasts differ by ~3e-3)
+    gold = golden_metrics["rollout64"]["metrics"]
+    assert res["SSIM"] == pytest.approx(gold["SSIM"], abs=2e-2)
+    assert res["CRPS"] == pytest.approx(gold["CRPS"], abs=2e-3)
+    assert 0.0 <= res["POD_0"] <= 1.0 and 0.0 <= res["FAR_0"] <= 1.0 and res["MSE"] > 0
+
+
+def test_decode_run_to_run(model):
+    """Same input twice: per-warp stats slots + fixed-order folds make the result reproducible up to
+    the fp64 atomic order (1e-16), i.e. practically bit-identical."""
+    torch.manual_seed(3)
+    z = torch.randn(2, 4, 8, 8, device=DEV)
+    a = model.decode(z)
+    b = model.decode(z)
+    assert rel_l2(a, b) < 1e-6

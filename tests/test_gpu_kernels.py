@@ -1,0 +1,164 @@
+"""-m gpu: every sm_100a kernel, called through the C ABI, against the CPU oracle / golden vectors."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import METRIC_CASES, metric_case_inputs
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from weatherforecastingtoolkit_b200 import _cabi
+    return _cabi.init(0)
+
+
+# ------------------------------------------------------------------ staging (bit-exact)
+@pytest.mark.parametrize("shape", [(2, 384, 384, 25), (1, 50, 70, 7), (1, 16, 16, 1), (3, 33, 17, 25)])
+def test_stage_vil_bitexact(lib, shape):
+    from oracle import akl_oracle as O
+    from weatherforecastingtoolkit_b200.rollout import stage_vil
+    g = torch.Generator().manual_seed(sum(shape))
+    u8 = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8)
+    want = O.stage_vil(u8).permute(0, 3, 1, 2).unsqueeze(2).contiguous()
+    got = stage_vil(u8.to(DEV))
+    assert got.shape == want.shape
+    assert torch.equal(got.cpu(), want)
+    got16 = stage_vil(u8.to(DEV), dtype=torch.float16)
+    assert torch.equal(got16.cpu(), want.to(torch.float16))
+
+
+def test_stage_vil_rejects_bad_input(lib):
+    from weatherforecastingtoolkit_b200.rollout import stage_vil
+    with pytest.raises(TypeError):
+        stage_vil(torch.zeros(1, 8, 8, 2, device=DEV))
+    with pytest.raises(RuntimeError):
+        stage_vil(torch.zeros(1, 8, 8, 2, dtype=torch.uint8))
+
+
+# ------------------------------------------------------------------ predictor
+@pytest.mark.parametrize("b,hw", [(1, 8), (3, 48)])
+def test_predictor_vs_oracle(lib, b, hw):
+    from oracle import akl_oracle as O
+    from weatherforecastingtoolkit_b200.rollout import LatentLinearPredictor
+    from weatherforecastingtoolkit_b200.synthetic import make_predictor_params
+    w, bias = make_predictor_params(seed=3)
+    torch.manual_seed(b)
+    lat = torch.randn(b, 25, 4, hw, hw)
+    pred_o, tgt_o, loss_o = O.predictor_rollout(lat, w, bias)
+    p = LatentLinearPredictor()
+    p.weight.data.copy_(w)
+    p.bias.data.copy_(bias)
+    pred, tgt, loss = p.rollout(lat.to(DEV))
+    assert torch.allclose(pred.cpu(), pred_o, atol=2e-6, rtol=1e-5)
+    assert torch.equal(tgt.cpu(), tgt_o)  # (x - last) + last, same fp32 ops
+    assert loss.item() == pytest.approx(loss_o.item(), rel=1e-5)
+
+
+# ------------------------------------------------------------------ metrics
+@pytest.mark.parametrize("name", METRIC_CASES)
+def test_metrics_vs_golden(lib, golden_metrics, name):
+    from weatherforecastingtoolkit_b200 import metrics as M
+    p, t = metric_case_inputs(name)
+    mp = M.metric_partials(p.to(DEV), t.to(DEV))
+    # bit-exact integer contingency counts (tp, fn, fp, tn) for 3 pools x 6 thresholds
+    assert mp.counts.tolist() == golden_metrics[name]["counts"]
+    got = M.scores_from_partials(mp)
+    want = golden_metrics[name]["metrics"]
+    assert list(got) == list(want)
+    for k, v in want.items():
+        if k.startswith(("CSI", "HSS", "paper_CSI", "paper_HSS")):
+            assert got[k] == v, k                      # bit-exact: same counts, same float32 ratio ops
+        elif "SSIM" in k:
+            assert got[k] == pytest.approx(v, abs=1e-3), k   # north_star tolerance; observed ~1e-6
+            assert got[k] == pytest.approx(v, abs=2e-5), k
+        elif "PSNR" in k:
+            assert got[k] == pytest.approx(v, rel=1e-5), k
+        else:  # CRPS == MAE
+            assert got[k] == pytest.approx(v, abs=1e-6), k
+
+
+def test_metrics_standalone_functions(lib):
+    from oracle import metrics_oracle as MO
+    from weatherforecastingtoolkit_b200 import metrics as M
+    p, t = metric_case_inputs("unclamped_1x3x50x70")   # NOT clamped by the stand-alone functions
+    pd, td = p.to(DEV), t.to(DEV)
+    th = 74 / 255
+    assert M.csi(pd, td, th) == MO.csi(p, t, th)
+    assert M.csi(pd, td, th, "avg", 4) == MO.csi(p, t, th, "avg", 4)
+    assert M.hss(pd, td, th, "avg", 16) == MO.hss(p, t, th, "avg", 16)
+    assert M.crps(pd, td) == pytest.approx(MO.crps(p, t), abs=1e-6)
+    assert M.crps(pd, td, "avg", 4) == pytest.approx(MO.crps(p, t, "avg", 4), abs=1e-6)
+    assert M.ssim(pd, td) == pytest.approx(MO.ssim(p, t), abs=2e-5)
+    assert M.psnr(pd, td) == pytest.approx(MO.psnr(p, t), rel=1e-5)
+    assert [float(v) for v in MO._hit_miss_fa_cn(p, t, th)] == list(M._hit_miss_fa_cn(pd, td, th))
+    with pytest.raises(NotImplementedError):
+        M.csi(pd, td, th, "max", 4)
+
+
+def test_metrics_edge_cases(lib):
+    from oracle import metrics_oracle as MO
+    from weatherforecastingtoolkit_b200 import metrics as M
+    # smallest legal image, one frame
+    torch.manual_seed(1)
+    p, t = torch.rand(1, 1, 1, 16, 19), torch.rand(1, 1, 1, 16, 19)
+    mp = M.metric_partials(p.to(DEV), t.to(DEV))
+    assert mp.counts.tolist() == MO.integer_counts(p, t).tolist()
+    assert mp.n_elems.tolist() == [16 * 19, 16, 1]
+    assert mp.ssim_sum == pytest.approx(MO.partials(p, t)["ssim_sum"], abs=1e-5)
+    # all-zero target: range 0 -> PSNR is -inf in torchmetrics' formula too
+    z = torch.zeros(1, 2, 1, 64, 64)
+    got = M.calc_metrics(torch.rand(1, 2, 1, 64, 64).to(DEV), z.to(DEV))
+    assert got["PSNR"] == -math.inf and got["CSI_0"] == 0.0
+    # identical inputs: SSIM 1, MAE 0
+    x = torch.rand(2, 3, 1, 96, 80)
+    got = M.calc_metrics(x.to(DEV), x.clone().to(DEV))
+    assert got["SSIM"] == pytest.approx(1.0, abs=1e-6) and got["CRPS"] == 0.0 and got["CSI_2"] == pytest.approx(1.0)
+    with pytest.raises(RuntimeError):
+        M.calc_metrics(torch.rand(1, 1, 1, 8, 8).to(DEV), torch.rand(1, 1, 1, 8, 8).to(DEV))  # < 11 px
+    with pytest.raises(RuntimeError):
+        M.calc_metrics(x, x)  # CPU tensors: no fallback
+
+
+def test_metrics_full_size_additivity(lib):
+    """BASELINE size (32 sequences x 12 frames x 384^2 = 56.6 M pixels, beyond float32-exact counting,
+    hazard H1): the counts of the whole batch equal the int64 sum of per-sequence counts, each of which is
+    checked against the oracle, and tp+fn+fp+tn == number of cells."""
+    from oracle import metrics_oracle as MO
+    from weatherforecastingtoolkit_b200 import metrics as M
+    from weatherforecastingtoolkit_b200.synthetic import make_vil_sequences
+    u8 = make_vil_sequences(32, 384, 384, 13, seed=77).to(DEV)
+    x = (u8.float() / 255).permute(0, 3, 1, 2).unsqueeze(2)
+    p, t = x[:, :12].contiguous(), x[:, 1:13].contiguous()
+    whole = M.metric_partials(p, t)
+    parts = [M.metric_partials(p[i:i + 1], t[i:i + 1]) for i in range(32)]
+    tot = parts[0]
+    for q in parts[1:]:
+        tot = tot + q
+    assert np.array_equal(whole.counts, tot.counts)
+    assert whole.counts[0].sum(axis=1).tolist() == [32 * 12 * 384 * 384] * 6
+    assert whole.counts[2].sum(axis=1).tolist() == [32 * 12 * 24 * 24] * 6
+    assert whole.counts[0].max() > 2 ** 24          # the regime where the reference's float32 sums round
+    for i in (0, 31):
+        assert parts[i].counts.tolist() == MO.integer_counts(p[i:i + 1].cpu(), t[i:i + 1].cpu()).tolist()
+    assert whole.ssim_sum == pytest.approx(tot.ssim_sum, rel=1e-9)
+    assert whole.abs_sum[0] == pytest.approx(tot.abs_sum[0], rel=1e-9)
+
+
+def test_metrics_deterministic(lib):
+    from weatherforecastingtoolkit_b200 import metrics as M
+    p, t = metric_case_inputs("rand_2x10x64")
+    a = M.metric_partials(p.to(DEV), t.to(DEV))
+    b = M.metric_partials(p.to(DEV), t.to(DEV))
+    assert np.array_equal(a.ints, b.ints) and np.array_equal(a.floats, b.floats)

@@ -1,0 +1,85 @@
+"""The CPU oracle reproduces the golden vectors that tests/golden/make_golden.py produced from
+the unmodified reference (runs anywhere; no GPU, no /root/reference)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import METRIC_CASES, metric_case_inputs
+from oracle import akl_oracle as O
+from oracle import metrics_oracle as MO
+from weatherforecastingtoolkit_b200.synthetic import make_predictor_params, make_vil_sequences
+
+
+def _frames(n, hw, seed):
+    u8 = make_vil_sequences(n, hw, hw, 1, seed=seed)
+    return O.stage_vil(u8).permute(0, 3, 1, 2).contiguous()
+
+
+def test_akl_64_bitexact(golden_akl, akl_weights):
+    cfg, sd = akl_weights
+    x = _frames(2, 64, 11)
+    with torch.no_grad():
+        m = O.akl_encode_moments(x, sd, cfg)
+        d = O.akl_decode(m[:, :4].contiguous(), sd, cfg)
+    np.testing.assert_allclose(m.numpy(), golden_akl["akl64_moments"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(d.numpy(), golden_akl["akl64_decoded"], rtol=0, atol=1e-5)
+
+
+def test_posterior_matches_reference_semantics():
+    m = torch.randn(2, 8, 4, 4) * 20
+    mean, logvar, std, var = O.posterior_from_moments(m)
+    assert logvar.max() <= 20 and logvar.min() >= -30
+    assert torch.equal(mean, m[:, :4])
+    assert torch.allclose(std * std, var, rtol=1e-5)
+
+
+def test_rollout64_latent_algebra(golden_akl):
+    """Predictor step (train.py:100-113) on the golden latents."""
+    lat = torch.from_numpy(golden_akl["rollout64_latents"])
+    w, b = make_predictor_params(seed=0)
+    pred, tgt, loss = O.predictor_rollout(lat, w, b)
+    np.testing.assert_allclose(pred.numpy(), golden_akl["rollout64_pred_latents"], atol=1e-6)
+    assert abs(loss.item() - float(golden_akl["rollout64_val_loss"])) < 1e-6
+    np.testing.assert_allclose(tgt.numpy(), lat[:, 13:].numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("name", METRIC_CASES)
+def test_metrics_oracle_vs_golden(golden_metrics, name):
+    p, t = metric_case_inputs(name)
+    got = MO.calc_metrics(p, t)
+    want = golden_metrics[name]["metrics"]
+    assert set(got) == set(want) and len(got) == 56
+    for k in want:
+        if np.isfinite(want[k]):
+            assert got[k] == pytest.approx(want[k], rel=1e-6, abs=1e-7), k
+        else:
+            assert not np.isfinite(got[k])
+    counts = MO.integer_counts(p, t)
+    assert counts.tolist() == golden_metrics[name]["counts"]
+
+
+def test_integer_counts_agree_with_float32_sums(golden_metrics):
+    """Below 2**24 the reference's float32 counts are exact and must equal the integer counts (H1)."""
+    for name in ("rand_2x10x64", "rand_2x12x384"):
+        c = golden_metrics[name]["counts"][0][1]
+        f = golden_metrics[name]["float32_counts_th1"]
+        assert [float(v) for v in c] == f
+
+
+def test_partials_consistency():
+    p, t = metric_case_inputs("rand_2x10x64")
+    pr = MO.partials(p, t)
+    m = MO.calc_metrics(p, t)
+    assert pr["abs_sum"][0] / pr["n_elems"][0] == pytest.approx(m["CRPS"], abs=1e-6)
+    assert pr["ssim_sum"] / pr["n_frames"] == pytest.approx(m["SSIM"], abs=1e-6)
+    assert pr["psnr_sum"] / pr["n_frames"] == pytest.approx(m["PSNR"], rel=1e-5)
+    assert pr["counts"][0].sum(axis=1).tolist() == [pr["n_elems"][0]] * 6
+
+
+def test_stage_vil_formula():
+    u8 = torch.arange(256, dtype=torch.uint8).reshape(1, 16, 16, 1)
+    x = O.stage_vil(u8)
+    scale = np.float32(1 / 255)
+    want = (np.arange(256, dtype=np.float32) * scale).reshape(1, 16, 16, 1)
+    assert np.array_equal(x.numpy(), want)
+    assert scale.view(np.uint32) == 0x3B808081

@@ -107,9 +107,9 @@ __device__ __forceinline__ void chunk_group_stats(const float (&v)[32], bool val
     s[0] += __shfl_xor_sync(0xffffffffu, s[0], off);
     q[0] += __shfl_xor_sync(0xffffffffu, q[0], off);
   }
-  if ((lane & (REM - 1)) == 0) {
-    atomicAdd(&s_dst[2 * grp + 0], s[0]);
-    atomicAdd(&s_dst[2 * grp + 1], q[0]);
+  if ((lane & (REM - 1)) == 0) {  // s_dst is this warp's private slot: plain RMW, fixed order
+    s_dst[2 * grp + 0] += s[0];
+    s_dst[2 * grp + 1] += q[0];
   }
 }
 
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [BN/4 groups max][2]
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [4 epilogue warps][BN/4 groups max][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t acc_phase = 0;
     const bool do_stats = p.stats != nullptr;
     if (do_stats) {
-      for (int i = et; i < BN / 2; i += 128) s_stats[i] = 0.f;
+      for (int i = et; i < 4 * (BN / 2); i += 128) s_stats[i] = 0.f;
       named_bar_sync(1, 128);
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
         }
         if (do_stats) {
-          float* dst = s_stats + 2 * (c0 >> p.cpg_log2);
+          float* dst = s_stats + quarter * (BN / 2) + 2 * (c0 >> p.cpg_log2);
           if (p.cpg_log2 == 2) chunk_group_stats<8>(v, valid, lane, dst);
           else if (p.cpg_log2 == 3) chunk_group_stats<4>(v, valid, lane, dst);
           else chunk_group_stats<2>(v, valid, lane, dst);
@@ -323,9 +323,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const int groups_in_tile = BN >> p.cpg_log2;
         if (et < 2 * groups_in_tile) {
           const int g = ((t.nt * BN) >> p.cpg_log2) + (et >> 1);
+          // fixed-order fold of the four warps' partials, then one fp64 reduction per (group, moment)
+          const float tot = ((s_stats[et] + s_stats[BN / 2 + et]) + s_stats[BN + et]) + s_stats[3 * (BN / 2) + et];
           atomicAdd(&p.stats[(static_cast<int64_t>(t.frame) * p.groups_total + g) * 2 + (et & 1)],
-                    static_cast<double>(s_stats[et]));
-          s_stats[et] = 0.f;
+                    static_cast<double>(tot));
+          s_stats[et] = s_stats[BN / 2 + et] = s_stats[BN + et] = s_stats[3 * (BN / 2) + et] = 0.f;
         }
         named_bar_sync(1, 128);
       }
@@ -355,7 +357,7 @@ struct ConvCfg<128> {
 template <int BN>
 constexpr size_t conv_smem_bytes() {
   return 1024 /*align slack*/ + ConvCfg<BN>::kStages * (kABytes + BN * kBlockK * 2) + (2 * ConvCfg<BN>::kStages + 4) * 8 +
-         16 + (BN / 2) * 4 + 64;
+         16 + 4 * (BN / 2) * 4 + 64;
 }
 
 }  // namespace wfk

@@ -19,12 +19,11 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(
     const float* __restrict__ in, int cin, int h, int w, const float* __restrict__ pre_w,
     const float* __restrict__ pre_b, const float* __restrict__ wt, const float* __restrict__ bias, int cout,
     __half* __restrict__ out, double* __restrict__ stats, int cpg, int pix_per_block) {
-  extern __shared__ float s_stat[];  // [cout/cpg][2]
+  __shared__ float s_part[256][4];  // per-thread (sum, sumsq) x up to 2 groups: reduced in a fixed order
   const int n = blockIdx.y;
   const int octets = cout >> 3;
   const int groups = stats ? cout / cpg : 0;
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) s_stat[i] = 0.f;
-  __syncthreads();
+  float ps[2] = {0.f, 0.f}, pq[2] = {0.f, 0.f};
   const int hw = h * w;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(hw, p_begin + pix_per_block);
@@ -84,33 +83,51 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(
     *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(n) * hw + p) * cout + oc) = u;
     if (stats != nullptr) {
       if (cpg >= 8) {
-        float s = 0.f, q = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          s += acc[j];
-          q = fmaf(acc[j], acc[j], q);
+          ps[0] += acc[j];
+          pq[0] = fmaf(acc[j], acc[j], pq[0]);
         }
-        atomicAdd(&s_stat[2 * (oc / cpg)], s);
-        atomicAdd(&s_stat[2 * (oc / cpg) + 1], q);
       } else {  // cpg == 4: two groups per octet
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          float s = 0.f, q = 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            s += acc[4 * g + j];
-            q = fmaf(acc[4 * g + j], acc[4 * g + j], q);
+            ps[g] += acc[4 * g + j];
+            pq[g] = fmaf(acc[4 * g + j], acc[4 * g + j], pq[g]);
           }
-          atomicAdd(&s_stat[2 * (oc / 4 + g)], s);
-          atomicAdd(&s_stat[2 * (oc / 4 + g) + 1], q);
         }
       }
     }
   }
   if (stats != nullptr) {
+    s_part[threadIdx.x][0] = ps[0];
+    s_part[threadIdx.x][1] = pq[0];
+    s_part[threadIdx.x][2] = ps[1];
+    s_part[threadIdx.x][3] = pq[1];
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
-      atomicAdd(&stats[static_cast<int64_t>(n) * groups * 2 + i], static_cast<double>(s_stat[i]));
+    // thread g folds every contributor of group g in thread-index order (deterministic)
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      double s = 0.0, q = 0.0;
+      if (cpg >= 8) {
+        const int o_begin = (g * cpg) >> 3, o_end = ((g + 1) * cpg) >> 3;
+        for (int t = 0; t < static_cast<int>(blockDim.x); ++t) {
+          const int o = t % octets;
+          if (o >= o_begin && o < o_end) {
+            s += s_part[t][0];
+            q += s_part[t][1];
+          }
+        }
+      } else {
+        const int o = g >> 1, sub = g & 1;
+        for (int t = o; t < static_cast<int>(blockDim.x); t += octets) {
+          s += s_part[t][2 * sub];
+          q += s_part[t][2 * sub + 1];
+        }
+      }
+      atomicAdd(&stats[(static_cast<int64_t>(n) * groups + g) * 2 + 0], s);
+      atomicAdd(&stats[(static_cast<int64_t>(n) * groups + g) * 2 + 1], q);
+    }
   }
 }
 
@@ -198,7 +215,7 @@ extern "C" int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int
   if (stats) WFK_REQUIRE(cpg >= 4 && cout % cpg == 0 && (cpg == 4 || cpg % 8 == 0), "cpg=%d unsupported", cpg);
   const int ppb = 64;
   dim3 grid((h * w + ppb - 1) / ppb, n);
-  const size_t smem = stats ? 2 * (cout / cpg) * sizeof(float) : 0;
+  const size_t smem = 0;
   wfk::conv3x3_small_cin_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       in, cin, h, w, pre_w, pre_b, weight, bias, cout, static_cast<__half*>(out), stats, cpg, ppb);
   return wfk::launched("conv3x3_small_cin_kernel");

@@ -31,6 +31,7 @@ struct MetricsParams {
   const float* tgt;
   int h, w, frames;
   int nthr;
+  int clamp01;
   float thr[WFK_MAX_THRESHOLDS];
   float gauss[11];
   float c1, c2;
@@ -148,8 +149,12 @@ __global__ void __launch_bounds__(kMetThreads, 2) metrics_tile_kernel(const __gr
     const int y = y0 - kHalo + r, x = x0 - kHalo + c;
     float pv = 0.f, tv = 0.f;
     if (y >= 0 && y < p.h && x >= 0 && x < p.w) {
-      pv = fminf(fmaxf(__ldg(pf + static_cast<int64_t>(y) * p.w + x), 0.f), 1.f);
-      tv = fminf(fmaxf(__ldg(tf + static_cast<int64_t>(y) * p.w + x), 0.f), 1.f);
+      pv = __ldg(pf + static_cast<int64_t>(y) * p.w + x);
+      tv = __ldg(tf + static_cast<int64_t>(y) * p.w + x);
+      if (p.clamp01) {
+        pv = fminf(fmaxf(pv, 0.f), 1.f);
+        tv = fminf(fmaxf(tv, 0.f), 1.f);
+      }
     }
     s.sp[r][c] = pv;
     s.st[r][c] = tv;
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(kMetThreads, 2) metrics_tile_kernel(const __gr
   __syncthreads();
 
   // ---- pool 1: counts, |d|, d^2, max(target) over the owned pixels
-  float abs1 = 0.f, sq = 0.f, mx = 0.f;
+  float abs1 = 0.f, sq = 0.f, mx = -INFINITY, mn = INFINITY;
   {
     int c[WFK_MAX_THRESHOLDS][3];
 #pragma unroll
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(kMetThreads, 2) metrics_tile_kernel(const __gr
         abs1 += fabsf(d);
         sq = fmaf(d, d, sq);
         mx = fmaxf(mx, tv);
+        mn = fminf(mn, tv);
       }
       nvalid += __popc(__ballot_sync(0xffffffffu, valid));
       count_thresholds(p, valid, pv, tv, c);
@@ -241,6 +247,7 @@ __global__ void __launch_bounds__(kMetThreads, 2) metrics_tile_kernel(const __gr
   abs1 = warp_sum(abs1);
   sq = warp_sum(sq);
   mx = warp_max(mx);
+  mn = -warp_max(-mn);
   ssim = warp_sum(ssim);
   abs4 = warp_sum(abs4);
   abs16 = warp_sum(abs16);
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__(kMetThreads, 2) metrics_tile_kernel(const __gr
     s.wred[warp][3] = ssim;
     s.wred[warp][4] = abs4;
     s.wred[warp][5] = abs16;
+    s.wred[warp][6] = mn;
   }
   __syncthreads();
   TileRec* rec = recs + (static_cast<int64_t>(f) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(kMetThreads, 2) metrics_tile_kernel(const __gr
     (&rec->counts[0][0][0])[i] = (&s.counts[0][0][0])[i];
   if (tid < WFK_NUM_POOLS) rec->n[tid] = s.n[tid];
   if (tid == 0) {
-    float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float r[6] = {0.f, 0.f, -INFINITY, 0.f, 0.f, 0.f};
     for (int wi = 0; wi < kMetWarps; ++wi) {
       r[0] += s.wred[wi][0];
       r[1] += s.wred[wi][1];
@@ -273,6 +281,9 @@ __global__ void __launch_bounds__(kMetThreads, 2) metrics_tile_kernel(const __gr
     rec->sq_sum = r[1];
     rec->max_t = r[2];
     rec->ssim_sum = r[3];
+    float mnr = INFINITY;
+    for (int wi = 0; wi < kMetWarps; ++wi) mnr = fminf(mnr, s.wred[wi][6]);
+    rec->pad2[0] = mnr;  // min(target)
   }
 }
 
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(256) metrics_finalize_kernel(const TileRec* __
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int f = tid; f < frames; f += blockDim.x) {
     double a1 = 0, a4 = 0, a16 = 0, sq = 0, ss = 0;
-    float mx = 0.f;
+    float mx = -INFINITY, mn = INFINITY;
     for (int t = 0; t < tiles_per_frame; ++t) {
       const TileRec& rec = recs[static_cast<int64_t>(f) * tiles_per_frame + t];
       a1 += rec.abs_sum[0];
@@ -315,9 +326,11 @@ __global__ void __launch_bounds__(256) metrics_finalize_kernel(const TileRec* __
       sq += rec.sq_sum;
       ss += rec.ssim_sum;
       mx = fmaxf(mx, rec.max_t);
+      mn = fminf(mn, rec.pad2[0]);
     }
     const double mse = sq / (static_cast<double>(h) * w);
-    const double range = static_cast<double>(mx);  // max(target.max(), 0) - min(target.min(), 0); target in [0,1]
+    // torchmetrics PeakSignalNoiseRatio(data_range=None): max(target.max(), 0) - min(target.min(), 0)
+    const double range = static_cast<double>(fmaxf(mx, 0.f)) - static_cast<double>(fminf(mn, 0.f));
     const double psnr = 10.0 * log10(range * range / mse);
     acc[0] += a1;
     acc[1] += a4;
@@ -365,8 +378,8 @@ extern "C" size_t wfk_metrics_workspace_bytes(int frames, int h, int w) {
 }
 
 extern "C" int wfk_metrics(const float* pred, const float* tgt, int frames, int h, int w, const float* thresholds,
-                           int n_thresholds, wfk_metric_partials* out, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           int n_thresholds, int clamp01, wfk_metric_partials* out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   WFK_REQUIRE_INIT();
   WFK_REQUIRE(pred && tgt && out && workspace && thresholds, "null pointer");
   WFK_REQUIRE(frames > 0 && frames <= 65535, "frames=%d unsupported (1..65535 per call)", frames);
@@ -380,6 +393,7 @@ extern "C" int wfk_metrics(const float* pred, const float* tgt, int frames, int 
   p.w = w;
   p.frames = frames;
   p.nthr = n_thresholds;
+  p.clamp01 = clamp01 ? 1 : 0;
   for (int i = 0; i < n_thresholds; ++i) p.thr[i] = thresholds[i];
   // torchmetrics _gaussian(kernel_size=11, sigma=1.5) in float32
   {

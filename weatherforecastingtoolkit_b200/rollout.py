@@ -1,0 +1,169 @@
+"""Path-B latent nowcast rollout behind the reference experiment's interfaces.
+
+Mirrors ``experiments/v1_experiments/pretrained_ae_linear_sevir/train.py`` (reference repo):
+``Autoencoder`` (the per-frame encode / decode wrapper, train.py:21-56), the ``nn.Linear(13*4,
+12*4)`` predictor with its residual framing (train.py:67, 101-113) and ``Model.validation_step``
+(train.py:100-120) up to ``log_metrics`` (pipeline/helpers.py:142-153). Host code only sequences
+kernels of libwfk_b200.so; PyTorch supplies device buffers, streams and ``torch.distributed``.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from . import metrics as wf_metrics
+from .models.autoencoderkl import AutoencoderKL
+from .synthetic import INPUT_FRAMES, PRED_FRAMES
+
+
+def _lib_for(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError("this path runs on a B200 only (no CPU fallback): pass CUDA tensors")
+    return _cabi.init(t.device.index if t.device.index is not None else 0)
+
+
+def stage_vil(batch_u8_nhwt: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """uint8 VIL [N, H, W, T] (SEVIR on-disk layout) -> normalised [N, T, 1, H, W].
+
+    Replaces ``SEVIRDataLoader.preprocess_data_dict`` + ``change_layout`` + the
+    ``permute(0,3,1,2).unsqueeze(2)`` of the train script (pipeline/datasets/sevir/sevir.py:626-666,
+    88-101; train.py:101): ``fl32(1/255) * float(x)``, bit-exact."""
+    if batch_u8_nhwt.dtype != torch.uint8 or batch_u8_nhwt.ndim != 4:
+        raise TypeError("expected a uint8 [N, H, W, T] tensor")
+    lib = _lib_for(batch_u8_nhwt)
+    x = batch_u8_nhwt.contiguous()
+    n, h, w, t = x.shape
+    if dtype not in (torch.float32, torch.float16):
+        raise ValueError("dtype must be float32 or float16")
+    out = torch.empty((n, t, 1, h, w), dtype=dtype, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _cabi.check(lib.wfk_stage_vil_u8(x.data_ptr(), n, h, w, t, out.data_ptr(), 0 if dtype == torch.float32 else 1,
+                                     stream), "wfk_stage_vil_u8")
+    return out
+
+
+class LatentLinearPredictor(nn.Linear):
+    """``self.predictor = nn.Linear(input_frames * 4, pred_frames * 4)`` (train.py:67). ``forward`` is
+    inherited (training stays PyTorch, out of scope); ``rollout`` is the fused inference kernel."""
+
+    def __init__(self, input_frames: int = INPUT_FRAMES, pred_frames: int = PRED_FRAMES, latent_channels: int = 4):
+        super().__init__(input_frames * latent_channels, pred_frames * latent_channels)
+        self.input_frames, self.pred_frames, self.latent_channels = input_frames, pred_frames, latent_channels
+
+    @torch.no_grad()
+    def rollout(self, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """v [B, t_in + t_out, C, h, w] fp32 latents -> (pred, tgt, val_loss): train.py:102-113 in one
+        pass (subtract last input frame, Linear per latent pixel, add it back; F.mse_loss of the
+        residual-space prediction)."""
+        lib = _lib_for(v)
+        b, t, c, h, w = v.shape
+        if t != self.input_frames + self.pred_frames or c != self.latent_channels:
+            raise ValueError(f"latents {tuple(v.shape)} do not match predictor "
+                             f"({self.input_frames}+{self.pred_frames} frames, {self.latent_channels} channels)")
+        v = v.detach().to(torch.float32).contiguous()
+        wt = self.weight.detach().to(device=v.device, dtype=torch.float32).contiguous()
+        bs = self.bias.detach().to(device=v.device, dtype=torch.float32).contiguous()
+        pred = torch.empty((b, self.pred_frames, c, h, w), dtype=torch.float32, device=v.device)
+        tgt = torch.empty_like(pred)
+        loss = torch.zeros(2, dtype=torch.float64, device=v.device)
+        stream = torch.cuda.current_stream(v.device).cuda_stream
+        _cabi.check(lib.wfk_predict_linear(v.data_ptr(), wt.data_ptr(), bs.data_ptr(), b, self.input_frames,
+                                           self.pred_frames, c, h * w, pred.data_ptr(), tgt.data_ptr(),
+                                           loss.data_ptr(), stream), "wfk_predict_linear")
+        return pred, tgt, (loss[0] / loss[1]).to(torch.float32)
+
+
+class Autoencoder(nn.Module):
+    """The train script's frozen-AE wrapper (train.py:21-56): ``encode([B,T,C,H,W]) -> [B,T,LC,h,w]``,
+    ``decode([B,T,LC,h,w]) -> [B,T,1,H,W]``. The reference loops over T with batch B; frames are
+    independent (GroupNorm is per sample), so they are processed ``frames_per_call`` at a time.
+
+    ``posterior``: "sample" reproduces the reference's ``.sample()`` (train.py:39, device RNG, not
+    reproducible CPU<->GPU); "mode" is the deterministic alternative the reference keeps
+    commented (train.py:42) and what parity tests use; a ``noise`` tensor can be injected instead."""
+
+    def __init__(self, config: dict, posterior: str = "sample", frames_per_call: int = 32):
+        super().__init__()
+        self.autoencoder = AutoencoderKL(**config)
+        self.autoencoder.eval()
+        self.scaling_factor = 0.18125  # train.py:26 (unused there too)
+        self.posterior = posterior
+        self.frames_per_call = int(frames_per_call)
+        self.autoencoder.requires_grad_(False)
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        b, t, c, h, w = x.shape
+        flat = x.reshape(b * t, c, h, w)
+        outs = []
+        for i in range(0, b * t, self.frames_per_call):
+            post = self.autoencoder.encode(flat[i:i + self.frames_per_call])
+            if noise is not None:
+                nz = noise.reshape(b * t, *noise.shape[2:])[i:i + self.frames_per_call]
+                outs.append(post.mean + post.std * nz)
+            elif self.posterior == "sample":
+                outs.append(post.sample())
+            else:
+                outs.append(post.mode())
+        z = torch.cat(outs, dim=0)
+        return z.reshape(b, t, *z.shape[1:])
+
+    @torch.no_grad()
+    def decode(self, x: torch.Tensor) -> torch.Tensor:
+        b, t, c, h, w = x.shape
+        flat = x.reshape(b * t, c, h, w)
+        outs = [self.autoencoder.decode(flat[i:i + self.frames_per_call]) for i in range(0, b * t, self.frames_per_call)]
+        y = torch.cat(outs, dim=0)
+        return y.reshape(b, t, *y.shape[1:])
+
+
+class PathBNowcast(nn.Module):
+    """``Model`` of the reference experiment, inference side (train.py:58-125)."""
+
+    def __init__(self, autoencoder_cfg: dict, input_frames: int = INPUT_FRAMES, pred_frames: int = PRED_FRAMES,
+                 posterior: str = "mode", frames_per_call: int = 32):
+        super().__init__()
+        self.autoencoder = Autoencoder(autoencoder_cfg, posterior=posterior, frames_per_call=frames_per_call)
+        self.input_frames, self.pred_frames = input_frames, pred_frames
+        self.predictor = LatentLinearPredictor(input_frames, pred_frames, autoencoder_cfg.get("latent_channels", 4))
+
+    def forward(self, x):
+        return self.predictor(x)
+
+    @torch.no_grad()
+    def validation_step(self, batch: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        """batch: [B, H, W, T] float32 in [0,1] (the reference loader's output) or uint8 (staged here).
+        Returns (decoded_pred, decoded_tgt, val_loss) -- the tensors train.py:115-120 hands to log_metrics."""
+        if batch.dtype == torch.uint8:
+            v = stage_vil(batch)
+        else:
+            v = batch.permute(0, 3, 1, 2).unsqueeze(2).contiguous()
+        lat = self.autoencoder.encode(v, noise=noise)
+        pred, tgt, loss = self.predictor.rollout(lat)
+        decoded_pred = self.autoencoder.decode(pred)
+        decoded_tgt = self.autoencoder.decode(tgt)
+        return decoded_pred, decoded_tgt, loss
+
+    @torch.no_grad()
+    def evaluate(self, batch: torch.Tensor, process_group=None, extended: bool = False) -> Dict[str, float]:
+        """validation_step + log_metrics' calc_metrics (pipeline/helpers.py:142-153), optionally summed
+        over the ranks of ``process_group`` with one all-reduce."""
+        dp, dt, loss = self.validation_step(batch)
+        res = wf_metrics.calc_metrics(dp, dt, extended=extended, process_group=process_group)
+        res["val_loss"] = float(loss.item())
+        return res
+
+
+def log_metrics(predictions, targets, tag, pl_module, process_group=None):
+    """``pipeline.helpers.log_metrics`` (helpers.py:142-153), same signature plus ``process_group``."""
+    if isinstance(predictions, torch.Tensor):
+        predictions = predictions.detach()
+    if isinstance(targets, torch.Tensor):
+        targets = targets.detach()
+    m = wf_metrics.calc_metrics(predictions, targets, process_group=process_group)
+    m = {f"{tag}_{k}": v for k, v in m.items()}
+    # counts were already summed over ranks, so the logged scalar needs no further reduction
+    pl_module.log_dict(m, on_step=True, on_epoch=True, sync_dist=process_group is None)
