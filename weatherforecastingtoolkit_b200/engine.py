@@ -25,6 +25,30 @@ F16 = torch.float16
 GN_EPS = 1e-6  # resnet_eps passed by Encoder/Decoder (vae.py:41,57,128)
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the tensor-core kernel (bench.py's roofline leg).
+    Events are recorded on the launching stream around every conv-GEMM launch; ``summary()`` must be
+    called after a synchronize. ``flops`` are NOMINAL (2*M*N*K of the reference layer), not what the
+    sub-pixel decomposition actually executes."""
+
+    def __init__(self):
+        self.records = []  # (what, nominal_flops, start_event, end_event)
+
+    def record(self, what, flops, start, end):
+        self.records.append((what, flops, start, end))
+
+    def summary(self):
+        tot_ms, tot_flops, n = 0.0, 0.0, 0
+        for _, fl, s, e in self.records:
+            tot_ms += s.elapsed_time(e)
+            tot_flops += fl
+            n += 1
+        return {"launches": n, "ms": tot_ms, "nominal_flops": tot_flops}
+
+
+TIMER: Optional[KernelTimer] = None  # set by bench.py
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -217,8 +241,16 @@ class _Program:
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.input.copy_(x)
         self.stats_arena.zero_()
-        for fn, args, what in self.ops:
-            _cabi.check(fn(*args, stream), what)
+        timer = TIMER
+        for fn, args, what, flops in self.ops:
+            if timer is not None and flops:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                _cabi.check(fn(*args, stream), what)
+                ev1.record()
+                timer.record(what, flops, ev0, ev1)
+            else:
+                _cabi.check(fn(*args, stream), what)
         return self.output.clone()
 
     # ------------------------------------------------------------------ helpers
@@ -229,14 +261,14 @@ class _Program:
             raise RuntimeError("stats arena exhausted")
         return s
 
-    def _add(self, fn, args, what):
-        self.ops.append((fn, tuple(args), what))
+    def _add(self, fn, args, what, flops=0.0):
+        self.ops.append((fn, tuple(args), what, float(flops)))
 
-    def _conv_plan(self, desc: ConvDesc, what: str):
+    def _conv_plan(self, desc: ConvDesc, what: str, nominal_flops: float):
         h = C.c_void_p()
         _cabi.check(self.lib.wfk_conv_plan_create(C.byref(desc), C.byref(h)), f"conv_plan_create[{what}]")
         self.plans.append(h)
-        self._add(self.lib.wfk_conv_plan_run, (h,), what)
+        self._add(self.lib.wfk_conv_plan_run, (h,), what, nominal_flops)
 
     @staticmethod
     def _view_nhwc(desc_view, t: torch.Tensor, n, h, w, c, pitch_c=None):
@@ -295,7 +327,8 @@ class _Program:
             d.taps_per_phase = 10
         d.a_frame_mul, d.b_frame_mul = 1, 0
         self._epilogue(d, bias, residual, out, None, stats, h, w, cout)
-        self._conv_plan(d, what)
+        k_total = 9 * cin + (shortcut[0].shape[3] if shortcut is not None else 0)
+        self._conv_plan(d, what, 2.0 * n * h * w * cout * k_total)
         return _Act(out, stats)
 
     def downsample(self, x: _Act, wname: str, bias: torch.Tensor, what="downsample") -> _Act:
@@ -326,7 +359,7 @@ class _Program:
                 k += 1
         d.a_frame_mul, d.b_frame_mul = 1, 0
         self._epilogue(d, bias, None, out, None, stats, oh, ow, c)
-        self._conv_plan(d, what)
+        self._conv_plan(d, what, 2.0 * n * oh * ow * c * 9 * c)
         return _Act(out, stats)
 
     def upsample(self, x: _Act, wname: str, bias: torch.Tensor, what="upsample") -> _Act:
@@ -350,7 +383,8 @@ class _Program:
                                                          ph * 4 + i * 2 + j, c // 64, 0)
         d.a_frame_mul, d.b_frame_mul = 1, 0
         self._epilogue(d, bias, None, out, None, stats, 2 * h, 2 * w, c, sy=2, sx=2)
-        self._conv_plan(d, what)
+        # nominal work of the reference layer: 3x3 conv on the upsampled (2h x 2w) tensor
+        self._conv_plan(d, what, 2.0 * n * (2 * h) * (2 * w) * c * 9 * c)
         return _Act(out, stats)
 
     def gn(self, x: _Act, pname: str, silu=True, what="groupnorm") -> torch.Tensor:
@@ -400,7 +434,7 @@ class _Program:
         d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
         d.a_frame_mul, d.b_frame_mul = 1, 0
         self._epilogue(d, t[p + ".qk.bias"], None, qk, None, None, 1, T, 2 * c)
-        self._conv_plan(d, p + ".qk")
+        self._conv_plan(d, p + ".qk", 2.0 * n * T * (2 * c) * c)
         # V^T = Wv . X^T : [n, c, T]   (value bias is added after P.V: softmax rows sum to 1)
         vt = self.pool.get((n, c, T))
         d = ConvDesc()
@@ -411,7 +445,7 @@ class _Program:
         d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
         d.a_frame_mul, d.b_frame_mul = 0, 1
         self._epilogue(d, None, None, vt, None, None, 1, c, T)
-        self._conv_plan(d, p + ".value^T")
+        self._conv_plan(d, p + ".value^T", 2.0 * n * T * c * c)
         self.pool.put(a)
         # scores = Q K^T (fp32), scale folded into the softmax
         scores = self.pool.get((n, T, T), torch.float32)
@@ -424,7 +458,7 @@ class _Program:
         d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
         d.a_frame_mul, d.b_frame_mul = 1, 1
         self._epilogue(d, None, None, None, scores, None, 1, T, T)
-        self._conv_plan(d, p + ".scores")
+        self._conv_plan(d, p + ".scores", 2.0 * n * T * T * c)
         probs = self.pool.get((n, T, T))
         self._add(self.lib.wfk_softmax_rows,
                   (scores.data_ptr(), n * T, T, 1.0 / math.sqrt(c), probs.data_ptr()), p + ".softmax")
@@ -439,7 +473,7 @@ class _Program:
         d.taps[0] = Tap(0, 0, 0, 0, 0, 0, (T + 63) // 64, 0)
         d.a_frame_mul, d.b_frame_mul = 1, 1
         self._epilogue(d, t[p + ".value.bias"], None, o, None, None, 1, T, c)
-        self._conv_plan(d, p + ".pv")
+        self._conv_plan(d, p + ".pv", 2.0 * n * T * T * c)
         self.pool.put(scores)
         self.pool.put(probs)
         self.pool.put(vt)
@@ -454,7 +488,7 @@ class _Program:
         d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
         d.a_frame_mul, d.b_frame_mul = 1, 0
         self._epilogue(d, t[p + ".proj_attn.bias"], x.t, out, None, stats, 1, T, c)
-        self._conv_plan(d, p + ".proj+res")
+        self._conv_plan(d, p + ".proj+res", 2.0 * n * T * c * c)
         self.pool.put(o)
         self.pool.put(x.t)
         return _Act(out, stats)
