@@ -182,6 +182,13 @@ int wfk_conv3x3_small_cout(const void* in, int n, int h, int w, int cin, const v
                            const float* bias, int cout, const float* post_w, const float* post_b, float* out,
                            void* stream);
 
+/* Decoder tail, fused: GroupNorm(groups, eps) + SiLU + conv3x3(c -> 1, pad 1).  Replaces
+ * conv_norm_out + conv_act + conv_out of Decoder.forward (vae.py:162-164).  x: [n, h, w, c] fp16 raw
+ * stream; stats as wfk_groupnorm_apply; weight: [9][c] fp32 (tap-major); out: [n, 1, h, w] fp32. */
+int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const float* gamma, const float* beta, int n,
+                           int h, int w, int c, int groups, float eps, const float* weight, float bias,
+                           float* out, void* stream);
+
 /* Row softmax: probs[r, :] = softmax(scale * scores[r, :]) in fp32, stored fp16.
  * Replaces torch.softmax(attention_scores.float(), dim=-1) (attention.py:171); `scale` is the
  * baddbmm alpha (attention.py:148, 168). */

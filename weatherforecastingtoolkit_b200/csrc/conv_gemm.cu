@@ -113,10 +113,10 @@ __device__ __forceinline__ void chunk_group_stats(const float (&v)[32], bool val
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int MB, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr int kBBytes = BN * kBlockK * 2;
-  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kStageBytes = MB * kABytes + kBBytes;  // MB pixel blocks (128 rows each) share one weight tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     tma_prefetch_desc(&p.a_map[0]);
     tma_prefetch_desc(&p.b_map[0]);
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * MB * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
-        const int x0 = t.tx * bw, y0 = t.ty * bh;
+        const int x0 = t.tx * bw, y0 = t.ty * bh * MB;
         for (int ti = 0; ti < p.taps_per_phase; ++ti) {
           const wfk_tap tap = p.taps[t.phase * p.taps_per_phase + ti];
           const CUtensorMap* am = &p.a_map[tap.src];
@@ -170,9 +170,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = smem + stage * kStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_5d(sa, am, &full_bar[stage], tap.c_off + kb * kBlockK, x0 + tap.dx, tap.q, y0 + tap.dy,
-                        t.frame * p.a_frame_mul);
-            tma_load_3d(sa + kABytes, bm, &full_bar[stage], kb * kBlockK, t.nt * BN,
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+              tma_load_5d(sa + mb * kABytes, am, &full_bar[stage], tap.c_off + kb * kBlockK, x0 + tap.dx, tap.q,
+                          y0 + mb * bh + tap.dy, t.frame * p.a_frame_mul);
+            tma_load_3d(sa + MB * kABytes, bm, &full_bar[stage], kb * kBlockK, t.nt * BN,
                         tap.b_slab + t.frame * p.b_frame_mul);
             if (++stage == STAGES) {
               stage = 0;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const TileCoord t = decode_tile(p, tile);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MB * BN);
         uint32_t accumulate = 0;
         for (int ti = 0; ti < p.taps_per_phase; ++ti) {
           const int kblocks = p.taps[t.phase * p.taps_per_phase + ti].kblocks;
@@ -201,11 +203,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-            const uint32_t b_addr = a_addr + kABytes;
+            const uint32_t b_addr = a_addr + MB * kABytes;
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
-              umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
-                       accumulate);
+              const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32);
+#pragma unroll
+              for (int mb = 0; mb < MB; ++mb)
+                umma_f16(d_tmem + mb * BN, umma_desc_sw128(a_addr + mb * kABytes + k * 32), bdesc, p.idesc, accumulate);
               accumulate = 1;
             }
             umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -233,8 +237,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
       const int row = quarter * 32 + lane;
-      const int py = t.ty * bh + (row >> p.bw_log2);
+#pragma unroll 1
+      for (int mb = 0; mb < MB; ++mb) {
+      const int py = (t.ty * MB + mb) * bh + (row >> p.bw_log2);
       const int px = t.tx * bw + (row & (bw - 1));
       const bool valid = (py < p.tile_h) && (px < p.tile_w);
       const int oy = py * p.out_sy + (t.phase >> 1);
@@ -242,9 +250,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
       const int64_t base = pix * p.ldc + static_cast<int64_t>(t.nt) * BN;
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>((acc * MB + mb) * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
 
       const int ncols = min(BN, p.n_total - t.nt * BN);  // N tail: columns >= ncols are padding
 #pragma unroll 1
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
         }
       }
+      }  // mb
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -338,7 +345,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc<2 * MB * BN>(tmem_base);
   }
 }
 
@@ -348,15 +355,17 @@ struct ConvCfg;
 template <>
 struct ConvCfg<256> {
   static constexpr int kStages = 4;
+  static constexpr int kMB = 1;
 };
 template <>
-struct ConvCfg<128> {
-  static constexpr int kStages = 6;
+struct ConvCfg<128> {  // N = 128: two 128-pixel blocks per tile so A+B bytes per MAC match the 128x256 tile
+  static constexpr int kStages = 4;
+  static constexpr int kMB = 2;
 };
 
 template <int BN>
 constexpr size_t conv_smem_bytes() {
-  return 1024 /*align slack*/ + ConvCfg<BN>::kStages * (kABytes + BN * kBlockK * 2) + (2 * ConvCfg<BN>::kStages + 4) * 8 +
+  return 1024 /*align slack*/ + ConvCfg<BN>::kStages * (ConvCfg<BN>::kMB * kABytes + BN * kBlockK * 2) + (2 * ConvCfg<BN>::kStages + 4) * 8 +
          16 + 4 * (BN / 2) * 4 + 64;
 }
 
@@ -450,12 +459,14 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
     return wfk::fail(WFK_ERR_INVALID, "stats need n_total (%d) to be a multiple of the N tile (%d)", d->n_total, plan->bn);
   }
 
+  const int mb_blocks = plan->bn == 256 ? wfk::ConvCfg<256>::kMB : wfk::ConvCfg<128>::kMB;
   // tile geometry: BW x BH = 128 output pixels, BW a power of two; minimise the padded area
   int best_log2 = 7;
   long best_area = -1;
   for (int l = 7; l >= 3; --l) {
     const int bw = 1 << l, bh = 128 >> l;
-    const long area = static_cast<long>((d->tile_w + bw - 1) / bw) * bw * (static_cast<long>((d->tile_h + bh - 1) / bh) * bh);
+    const int bhe = bh * mb_blocks;
+    const long area = static_cast<long>((d->tile_w + bw - 1) / bw) * bw * (static_cast<long>((d->tile_h + bhe - 1) / bhe) * bhe);
     if (best_area < 0 || area < best_area) {
       best_area = area;
       best_log2 = l;
@@ -467,7 +478,7 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.tile_h = d->tile_h;
   p.tile_w = d->tile_w;
   p.tiles_x = (d->tile_w + bw - 1) / bw;
-  p.tiles_y = (d->tile_h + bh - 1) / bh;
+  p.tiles_y = (d->tile_h + bh * mb_blocks - 1) / (bh * mb_blocks);
   p.tiles_n = (d->n_total + plan->bn - 1) / plan->bn;
   p.n_total = d->n_total;
   p.num_phases = d->num_phases;
@@ -518,19 +529,19 @@ extern "C" int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static bool attr_set = false;
   if (!attr_set) {
-    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv_gemm_kernel<256, wfk::ConvCfg<256>::kStages>,
+    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv_gemm_kernel<256, wfk::ConvCfg<256>::kMB, wfk::ConvCfg<256>::kStages>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(wfk::conv_smem_bytes<256>())));
-    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv_gemm_kernel<128, wfk::ConvCfg<128>::kStages>,
+    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv_gemm_kernel<128, wfk::ConvCfg<128>::kMB, wfk::ConvCfg<128>::kStages>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(wfk::conv_smem_bytes<128>())));
     attr_set = true;
   }
   if (plan->bn == 256) {
-    wfk::conv_gemm_kernel<256, wfk::ConvCfg<256>::kStages>
+    wfk::conv_gemm_kernel<256, wfk::ConvCfg<256>::kMB, wfk::ConvCfg<256>::kStages>
         <<<plan->grid, wfk::kConvThreads, wfk::conv_smem_bytes<256>(), s>>>(plan->params);
   } else {
-    wfk::conv_gemm_kernel<128, wfk::ConvCfg<128>::kStages>
+    wfk::conv_gemm_kernel<128, wfk::ConvCfg<128>::kMB, wfk::ConvCfg<128>::kStages>
         <<<plan->grid, wfk::kConvThreads, wfk::conv_smem_bytes<128>(), s>>>(plan->params);
   }
   return wfk::launched("conv_gemm_kernel");

@@ -12,23 +12,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int hw, int c, int groups,
                                                        float eps, int apply_silu, __half* __restrict__ out, int ppb) {
-  extern __shared__ float s_ab[];  // a[c], b[c]
+  extern __shared__ float s_ab[];  // a[c], b[c], then mean[groups], rstd[groups]
   float* s_a = s_ab;
   float* s_b = s_ab + c;
+  float* s_mean = s_b + c;
+  float* s_rstd = s_mean + groups;
   const int n = blockIdx.y;
   const int cpg = c / groups;
-  const double cnt = static_cast<double>(cpg) * hw;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    const int g = ch / cpg;
+  if (threadIdx.x < groups) {  // fp64 only once per group, not per channel
+    const double cnt = static_cast<double>(cpg) * hw;
+    const int g = threadIdx.x;
     const double sum = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 0];
     const double sq = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 1];
     const double mean = sum / cnt;
     double var = sq / cnt - mean * mean;
     var = var < 0.0 ? 0.0 : var;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float a = rstd * gamma[ch];
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(rsqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const int g = ch / cpg;
+    const float a = s_rstd[g] * gamma[ch];
     s_a[ch] = a;
-    s_b[ch] = beta[ch] - static_cast<float>(mean) * a;
+    s_b[ch] = beta[ch] - s_mean[g] * a;
   }
   __syncthreads();
   const int vpp = c >> 3;  // 16-byte vectors per pixel
@@ -37,22 +44,42 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
   const int total = npix * vpp;
   const uint4* xin = reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(n) * hw + p0) * c);
   uint4* yout = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(n) * hw + p0) * c);
-  for (int v = threadIdx.x; v < total; v += blockDim.x) {
-    const int cv = (v % vpp) << 3;
-    uint4 u = __ldg(xin + v);
-    __half2* h2 = reinterpret_cast<__half2*>(&u);
+  // blockDim.x (256) is a multiple of vpp for every supported c, so a thread's channel slice is fixed:
+  // its 8 scale/shift pairs live in registers and the loop is pure streaming (4 loads in flight).
+  const int cv = (threadIdx.x % vpp) << 3;
+  float ra[8], rb[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = __half22float2(h2[e]);
-      f.x = fmaf(f.x, s_a[cv + 2 * e], s_b[cv + 2 * e]);
-      f.y = fmaf(f.y, s_a[cv + 2 * e + 1], s_b[cv + 2 * e + 1]);
-      if (apply_silu) {
-        f.x = __fdividef(f.x, 1.f + __expf(-f.x));
-        f.y = __fdividef(f.y, 1.f + __expf(-f.y));
-      }
-      h2[e] = __floats2half2_rn(f.x, f.y);
+  for (int j = 0; j < 8; ++j) {
+    ra[j] = s_a[cv + j];
+    rb[j] = s_b[cv + j];
+  }
+  constexpr int U = 4;
+  for (int v0 = threadIdx.x; v0 < total; v0 += U * blockDim.x) {
+    uint4 u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int v = v0 + k * blockDim.x;
+      if (v < total) u[k] = __ldg(xin + v);
     }
-    yout[v] = u;
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int v = v0 + k * blockDim.x;
+      if (v < total) {
+        __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __half22float2(h2[e]);
+          f.x = fmaf(f.x, ra[2 * e], rb[2 * e]);
+          f.y = fmaf(f.y, ra[2 * e + 1], rb[2 * e + 1]);
+          if (apply_silu) {
+            f.x = __fdividef(f.x, 1.f + __expf(-f.x));
+            f.y = __fdividef(f.y, 1.f + __expf(-f.y));
+          }
+          h2[e] = __floats2half2_rn(f.x, f.y);
+        }
+        yout[v] = u[k];
+      }
+    }
   }
 }
 
@@ -103,12 +130,13 @@ extern "C" int wfk_groupnorm_apply(const void* x, const double* stats, const flo
   WFK_REQUIRE_INIT();
   WFK_REQUIRE(x && stats && gamma && beta && out, "null pointer");
   WFK_REQUIRE(n > 0 && hw > 0 && c > 0 && groups > 0, "empty problem");
-  WFK_REQUIRE(c % 8 == 0 && c % groups == 0 && c <= 4096, "unsupported channel count c=%d groups=%d", c, groups);
+  WFK_REQUIRE(c % 8 == 0 && c % groups == 0 && c <= 2048 && 256 % (c / 8) == 0 && groups <= 256,
+              "unsupported channel count c=%d groups=%d", c, groups);
   WFK_REQUIRE(n <= 65535, "n too large");
-  int ppb = 16384 / c;
+  int ppb = 65536 / c;  // 128 KB of fp16 per block: amortises the per-block scale/shift prologue
   if (ppb < 1) ppb = 1;
   dim3 grid((hw + ppb - 1) / ppb, n);
-  wfk::gn_apply_kernel<<<grid, 256, 2 * c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  wfk::gn_apply_kernel<<<grid, 256, (2 * c + 2 * groups) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), stats, gamma, beta, hw, c, groups, eps, apply_silu, static_cast<__half*>(out), ppb);
   return wfk::launched("gn_apply_kernel");
 }

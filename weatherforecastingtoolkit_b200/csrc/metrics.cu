@@ -287,84 +287,90 @@ __global__ void __launch_bounds__(kMetThreads, 2) metrics_tile_kernel(const __gr
   }
 }
 
-// Fixed-order reduction of the per-tile records: thread f handles frame f (tiles in index order),
-// then one thread folds the per-frame values in frame order.
-__global__ void __launch_bounds__(256) metrics_finalize_kernel(const TileRec* __restrict__ recs, int frames,
-                                                               int tiles_per_frame, int h, int w, int nthr,
-                                                               wfk_metric_partials* __restrict__ out) {
-  __shared__ unsigned long long s_counts[WFK_NUM_POOLS][WFK_MAX_THRESHOLDS][3];
-  __shared__ unsigned long long s_n[WFK_NUM_POOLS];
-  __shared__ double s_acc[6];  // abs1, abs4, abs16, sq, ssim, psnr
-  const int tid = threadIdx.x;
-  for (int i = tid; i < WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3; i += blockDim.x) (&s_counts[0][0][0])[i] = 0ull;
-  if (tid < WFK_NUM_POOLS) s_n[tid] = 0ull;
-  if (tid < 6) s_acc[tid] = 0.0;
-  __syncthreads();
-  // integer counts: order does not matter
-  const int64_t total_recs = static_cast<int64_t>(frames) * tiles_per_frame;
-  for (int64_t r = tid; r < total_recs; r += blockDim.x) {
-    const TileRec& rec = recs[r];
-    for (int pl = 0; pl < WFK_NUM_POOLS; ++pl) {
-      for (int k = 0; k < nthr; ++k)
-        for (int j = 0; j < 3; ++j)
-          if (rec.counts[pl][k][j]) atomicAdd(&s_counts[pl][k][j], static_cast<unsigned long long>(rec.counts[pl][k][j]));
-      atomicAdd(&s_n[pl], static_cast<unsigned long long>(rec.n[pl]));
-    }
-  }
-  __syncthreads();
-  // float sums: frame by frame in a fixed order (serial over frames per lane, then serial fold)
-  __shared__ double s_frame[256][6];
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int f = tid; f < frames; f += blockDim.x) {
-    double a1 = 0, a4 = 0, a16 = 0, sq = 0, ss = 0;
-    float mx = -INFINITY, mn = INFINITY;
+// Reduction of the per-tile records in a fixed order (deterministic float results), two levels:
+// (1) one block per frame folds that frame's tiles into a FrameRec (and forms the per-frame SSIM / PSNR),
+// (2) one block folds the FrameRecs in frame order into the output struct.
+constexpr int kNumInt = WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3 + WFK_NUM_POOLS;  // 75
+
+struct FrameRec {
+  long long ints[kNumInt + 1];  // counts (c_pt, c_p, c_t) then n per pool
+  double f[6];                  // abs1, abs4, abs16, sq, ssim_frame, psnr_frame
+};
+
+__global__ void __launch_bounds__(128) metrics_frame_kernel(const TileRec* __restrict__ recs, int tiles_per_frame,
+                                                            int h, int w, FrameRec* __restrict__ frames_out) {
+  __shared__ float s_f[8];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const TileRec* fr = recs + static_cast<int64_t>(f) * tiles_per_frame;
+  FrameRec* out = frames_out + f;
+  if (tid < kNumInt) {
+    long long acc = 0;
     for (int t = 0; t < tiles_per_frame; ++t) {
-      const TileRec& rec = recs[static_cast<int64_t>(f) * tiles_per_frame + t];
-      a1 += rec.abs_sum[0];
-      a4 += rec.abs_sum[1];
-      a16 += rec.abs_sum[2];
-      sq += rec.sq_sum;
-      ss += rec.ssim_sum;
-      mx = fmaxf(mx, rec.max_t);
-      mn = fminf(mn, rec.pad2[0]);
+      const int* ip = (tid < kNumInt - WFK_NUM_POOLS) ? (&fr[t].counts[0][0][0] + tid) : (&fr[t].n[0] + (tid - (kNumInt - WFK_NUM_POOLS)));
+      acc += *ip;
     }
-    const double mse = sq / (static_cast<double>(h) * w);
-    // torchmetrics PeakSignalNoiseRatio(data_range=None): max(target.max(), 0) - min(target.min(), 0)
-    const double range = static_cast<double>(fmaxf(mx, 0.f)) - static_cast<double>(fminf(mn, 0.f));
-    const double psnr = 10.0 * log10(range * range / mse);
-    acc[0] += a1;
-    acc[1] += a4;
-    acc[2] += a16;
-    acc[3] += sq;
-    acc[4] += ss / (static_cast<double>(h - 2 * kHalo) * (w - 2 * kHalo));
-    acc[5] += psnr;
+    out->ints[tid] = acc;
+  } else if (tid >= 96 && tid < 96 + 7) {
+    const int j = tid - 96;  // abs1, abs4, abs16, sq, ssim, max, min
+    double acc = (j == 5) ? -INFINITY : ((j == 6) ? INFINITY : 0.0);
+    for (int t = 0; t < tiles_per_frame; ++t) {
+      const TileRec& r = fr[t];
+      const float v = j == 0 ? r.abs_sum[0] : j == 1 ? r.abs_sum[1] : j == 2 ? r.abs_sum[2] : j == 3 ? r.sq_sum
+                    : j == 4 ? r.ssim_sum : j == 5 ? r.max_t : r.pad2[0];
+      if (j == 5) acc = fmax(acc, static_cast<double>(v));
+      else if (j == 6) acc = fmin(acc, static_cast<double>(v));
+      else acc += v;
+    }
+    if (j < 4) out->f[j] = acc;
+    if (j == 4) out->f[4] = acc / (static_cast<double>(h - 2 * kHalo) * (w - 2 * kHalo));
+    if (j == 3) s_f[0] = static_cast<float>(acc / (static_cast<double>(h) * w));  // mse (double kept below)
+    if (j == 5) s_f[1] = static_cast<float>(acc);
+    if (j == 6) s_f[2] = static_cast<float>(acc);
   }
-  for (int j = 0; j < 6; ++j) s_frame[tid][j] = acc[j];
   __syncthreads();
   if (tid == 0) {
-    double tot[6] = {0, 0, 0, 0, 0, 0};
-    const int nt = frames < static_cast<int>(blockDim.x) ? frames : static_cast<int>(blockDim.x);
-    for (int i = 0; i < nt; ++i)
-      for (int j = 0; j < 6; ++j) tot[j] += s_frame[i][j];
+    // torchmetrics PeakSignalNoiseRatio(data_range=None): max(target.max(), 0) - min(target.min(), 0)
+    const double mse = out->f[3] / (static_cast<double>(h) * w);
+    const double range = static_cast<double>(fmaxf(s_f[1], 0.f)) - static_cast<double>(fminf(s_f[2], 0.f));
+    out->f[5] = 10.0 * log10(range * range / mse);
+  }
+}
+
+__global__ void __launch_bounds__(128) metrics_finalize_kernel(const FrameRec* __restrict__ fr, int frames, int nthr,
+                                                               wfk_metric_partials* __restrict__ out) {
+  __shared__ long long s_i[kNumInt];
+  __shared__ double s_d[6];
+  const int tid = threadIdx.x;
+  if (tid < kNumInt) {
+    long long acc = 0;
+    for (int f = 0; f < frames; ++f) acc += fr[f].ints[tid];
+    s_i[tid] = acc;
+  } else if (tid >= 96 && tid < 102) {
+    double acc = 0.0;
+    for (int f = 0; f < frames; ++f) acc += fr[f].f[tid - 96];
+    s_d[tid - 96] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
     for (int pl = 0; pl < WFK_NUM_POOLS; ++pl) {
+      const long long n = s_i[kNumInt - WFK_NUM_POOLS + pl];
       for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) {
-        const long long c_pt = static_cast<long long>(s_counts[pl][k][0]);
-        const long long c_p = static_cast<long long>(s_counts[pl][k][1]);
-        const long long c_t = static_cast<long long>(s_counts[pl][k][2]);
-        const long long n = static_cast<long long>(s_n[pl]);
+        const long long c_pt = s_i[(pl * WFK_MAX_THRESHOLDS + k) * 3 + 0];
+        const long long c_p = s_i[(pl * WFK_MAX_THRESHOLDS + k) * 3 + 1];
+        const long long c_t = s_i[(pl * WFK_MAX_THRESHOLDS + k) * 3 + 2];
         const bool on = k < nthr;
         out->counts[pl][k][0] = on ? c_pt : 0;                 // tp
         out->counts[pl][k][1] = on ? c_t - c_pt : 0;           // fn  (target yes, pred no)
         out->counts[pl][k][2] = on ? c_p - c_pt : 0;           // fp  (pred yes, target no)
         out->counts[pl][k][3] = on ? n - c_p - c_t + c_pt : 0; // tn
       }
-      out->n_elems[pl] = static_cast<long long>(s_n[pl]);
-      out->abs_sum[pl] = tot[pl];
+      out->n_elems[pl] = n;
+      out->abs_sum[pl] = s_d[pl];
     }
     out->n_frames = frames;
-    out->sq_sum = tot[3];
-    out->ssim_sum = tot[4];
-    out->psnr_sum = tot[5];
+    out->sq_sum = s_d[3];
+    out->ssim_sum = s_d[4];
+    out->psnr_sum = s_d[5];
     out->reserved[0] = out->reserved[1] = 0.0;
   }
 }
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(256) metrics_finalize_kernel(const TileRec* __
 extern "C" size_t wfk_metrics_workspace_bytes(int frames, int h, int w) {
   if (frames <= 0 || h <= 0 || w <= 0) return 0;
   const size_t tiles = static_cast<size_t>((h + wfk::kTS - 1) / wfk::kTS) * ((w + wfk::kTS - 1) / wfk::kTS);
-  return tiles * static_cast<size_t>(frames) * sizeof(wfk::TileRec);
+  return tiles * static_cast<size_t>(frames) * sizeof(wfk::TileRec) + static_cast<size_t>(frames) * sizeof(wfk::FrameRec) + 256;
 }
 
 extern "C" int wfk_metrics(const float* pred, const float* tgt, int frames, int h, int w, const float* thresholds,
@@ -419,7 +425,11 @@ extern "C" int wfk_metrics(const float* pred, const float* tgt, int frames, int 
       p, static_cast<wfk::TileRec*>(workspace));
   int rc = wfk::launched("metrics_tile_kernel");
   if (rc != WFK_OK) return rc;
-  wfk::metrics_finalize_kernel<<<1, 256, 0, s>>>(static_cast<const wfk::TileRec*>(workspace), frames, tx * ty, h, w,
-                                                 n_thresholds, out);
+  const size_t tile_bytes = (static_cast<size_t>(tx) * ty * frames * sizeof(wfk::TileRec) + 255) & ~static_cast<size_t>(255);
+  wfk::FrameRec* frs = reinterpret_cast<wfk::FrameRec*>(static_cast<uint8_t*>(workspace) + tile_bytes);
+  wfk::metrics_frame_kernel<<<frames, 128, 0, s>>>(static_cast<const wfk::TileRec*>(workspace), tx * ty, h, w, frs);
+  rc = wfk::launched("metrics_frame_kernel");
+  if (rc != WFK_OK) return rc;
+  wfk::metrics_finalize_kernel<<<1, 128, 0, s>>>(frs, frames, n_thresholds, out);
   return wfk::launched("metrics_finalize_kernel");
 }

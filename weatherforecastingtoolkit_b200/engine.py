@@ -109,6 +109,8 @@ class PackedAKL:
                 elif mod == "encoder.conv_out" or mod == "decoder.conv_out":
                     # direct kernel: [cout][9][cin] fp16
                     self.t[mod + ".w_direct"] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin).contiguous().to(F16)
+                    if cout == 1:  # fused GroupNorm+SiLU+conv tail: [9][cin] fp32
+                        self.t[mod + ".w_tap"] = w.permute(0, 2, 3, 1).reshape(9, cin).contiguous()
                 elif ".upsamplers." in mod:
                     self.t[mod + ".w_phase"] = self._phase_weights(w)
                 else:
@@ -557,10 +559,19 @@ class _Program:
                 y = self.upsample(x, p + ".w_phase", t[p + ".bias"], what=p)
                 self.pool.put(x.t)
                 x = y
-        a = self.gn(x, "decoder.conv_norm_out", what="decoder.conv_norm_out")
-        self.pool.put(x.t)
         _, H, W, c = x.shape
         out = torch.empty((n, eng.out_ch, H, W), dtype=torch.float32, device=self.dev)
+        if eng.out_ch == 1:
+            # fused GroupNorm + SiLU + conv_out: one read of the raw stream, no normalised copy
+            self._add(self.lib.wfk_gn_silu_conv3x3_c1,
+                      (x.t.data_ptr(), x.stats.data_ptr(), t["decoder.conv_norm_out.weight"].data_ptr(),
+                       t["decoder.conv_norm_out.bias"].data_ptr(), n, H, W, c, eng.groups, GN_EPS,
+                       t["decoder.conv_out.w_tap"].data_ptr(), float(t["decoder.conv_out.bias"][0].item()),
+                       out.data_ptr()), "decoder.conv_norm_out+silu+conv_out")
+            self.keep.append(x.t)
+            return out
+        a = self.gn(x, "decoder.conv_norm_out", what="decoder.conv_norm_out")
+        self.pool.put(x.t)
         self._add(self.lib.wfk_conv3x3_small_cout,
                   (a.data_ptr(), n, H, W, c, t["decoder.conv_out.w_direct"].data_ptr(),
                    t["decoder.conv_out.bias"].data_ptr(), eng.out_ch, None, None, out.data_ptr()),
