@@ -258,6 +258,18 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     scores = M.scores_from_partials(M._to_host(last, 6), extended=True)
+    if args.breakdown and rank == 0:
+        agg = {}
+        for what, fl, s0, s1 in timer.records:
+            a = agg.setdefault(what, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += s0.elapsed_time(s1)
+            a[2] += fl
+        rows = [{"layer": k, "launches": v[0], "ms": v[1], "nominal_tflops": v[2] / (v[1] / 1e3) / 1e12 if v[1] > 0 else 0.0,
+                 "gflop_per_launch": v[2] / v[0] / 1e9} for k, v in agg.items()]
+        rows.sort(key=lambda r: -r["ms"])
+        with open(args.breakdown, "w") as f:
+            json.dump(rows, f, indent=1)
 
     # ---- timed region 2: end to end through the public API, HOST input, score dict read back
     barrier()
@@ -324,6 +336,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="sequences per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--frames-per-call", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--breakdown", default=None, help="write a per-layer conv-GEMM timing table (JSON) to this path")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

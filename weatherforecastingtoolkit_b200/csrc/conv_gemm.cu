@@ -27,7 +27,9 @@ namespace wfk {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // fp16 elements = one 128 B swizzle row
-constexpr int kConvThreads = 192;
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter: latency hiding by TLP
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kConvThreads = 64 + kEpiThreads;
 constexpr int kABytes = kBlockM * kBlockK * 2;
 
 struct ConvKernelParams {
@@ -124,7 +126,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [4 epilogue warps][BN/4 groups max][2]
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [kEpiWarps][BN/4 groups max][2]
+  float* s_bias = s_stats + kEpiWarps * (BN / 2);                     // [BN] bias of the current N tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -187,36 +190,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer
+      // The issue loop must sustain one tcgen05.mma per 64 tensor-core cycles (N = 128), so descriptors
+      // are built incrementally: the high word (SBO, version, swizzle) is constant, the low word is the
+      // stage's start address >> 4 plus (bytes >> 4) per K slice / pixel block.
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t lo0 = static_cast<uint32_t>(desc0);
+      const uint32_t idesc = p.idesc;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
+        int kb_total = 0;
+        for (int ti = 0; ti < p.taps_per_phase; ++ti) kb_total += p.taps[t.phase * p.taps_per_phase + ti].kblocks;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MB * BN);
         uint32_t accumulate = 0;
-        for (int ti = 0; ti < p.taps_per_phase; ++ti) {
-          const int kblocks = p.taps[t.phase * p.taps_per_phase + ti].kblocks;
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-            const uint32_t b_addr = a_addr + MB * kABytes;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + ((MB * kABytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
 #pragma unroll
-              for (int mb = 0; mb < MB; ++mb)
-                umma_f16(d_tmem + mb * BN, umma_desc_sw128(a_addr + mb * kABytes + k * 32), bdesc, p.idesc, accumulate);
-              accumulate = 1;
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + static_cast<uint32_t>(mb * (kABytes >> 4) + 2 * k));
+              umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
+            accumulate = 1;  // after BOTH pixel blocks have issued their first (overwriting) MMA
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
@@ -227,60 +238,97 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;       // 0..127
+    const int et = threadIdx.x - 64;       // 0..kEpiThreads-1
+    const int ew = warp - 2;               // epilogue warp index: owns chunks ew/4, ew/4 + 2, ...
+    const int part = ew >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool do_stats = p.stats != nullptr;
+    int bias_nt = -1;
     if (do_stats) {
-      for (int i = et; i < 4 * (BN / 2); i += 128) s_stats[i] = 0.f;
-      named_bar_sync(1, 128);
+      for (int i = et; i < kEpiWarps * (BN / 2); i += kEpiThreads) s_stats[i] = 0.f;
+      named_bar_sync(1, kEpiThreads);
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
+      const int row = quarter * 32 + lane;
+      if (t.nt != bias_nt) {  // stage this N tile's bias once (smem broadcast reads in the chunk loop)
+        named_bar_sync(2, kEpiThreads);
+        for (int i = et; i < BN; i += kEpiThreads) {
+          const int c = t.nt * BN + i;
+          s_bias[i] = (p.bias != nullptr && c < p.n_total) ? __ldg(p.bias + c) : 0.f;
+        }
+        named_bar_sync(2, kEpiThreads);
+        bias_nt = t.nt;
+      }
+      // output coordinates of this thread's row in each of the MB pixel blocks
+      bool valid_mb[2] = {false, false};
+      int64_t base_mb[2] = {0, 0};
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int py = (t.ty * MB + mb) * bh + (row >> p.bw_log2);
+        const int px = t.tx * bw + (row & (bw - 1));
+        valid_mb[mb] = (py < p.tile_h) && (px < p.tile_w);
+        const int oy = py * p.out_sy + (t.phase >> 1);
+        const int ox = px * p.out_sx + (t.phase & 1);
+        const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
+        base_mb[mb] = pix * p.ldc + static_cast<int64_t>(t.nt) * BN;
+      }
+      const int ncols = min(BN, p.n_total - t.nt * BN);  // N tail: columns >= ncols are padding
+      const int nchunks = (ncols + 31) >> 5;
+      const int total_it = MB * nchunks;
+      const bool has_res = p.residual != nullptr;
+      // residual values are prefetched one chunk ahead (and before the accumulator is even ready) so
+      // their global-memory latency is off the epilogue's critical path
+      uint4 rnext[4];
+      auto issue_residual = [&](int it) {
+        const int mb_i = (MB == 1) ? 0 : (it >= nchunks ? 1 : 0);
+        const int c0_i = (it - mb_i * nchunks) << 5;
+        const bool v_i = (MB == 1) ? valid_mb[0] : (mb_i ? valid_mb[1] : valid_mb[0]);
+        const int64_t b_i = (MB == 1) ? base_mb[0] : (mb_i ? base_mb[1] : base_mb[0]);
+        if (has_res && v_i) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + b_i + c0_i);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c0_i + 8 * j < ncols) rnext[j] = __ldg(rp + j);
+        }
+      };
+      constexpr int kParts = kEpiWarps / 4;
+      if (part < total_it) issue_residual(part);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = quarter * 32 + lane;
+      const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * MB * BN);
 #pragma unroll 1
-      for (int mb = 0; mb < MB; ++mb) {
-      const int py = (t.ty * MB + mb) * bh + (row >> p.bw_log2);
-      const int px = t.tx * bw + (row & (bw - 1));
-      const bool valid = (py < p.tile_h) && (px < p.tile_w);
-      const int oy = py * p.out_sy + (t.phase >> 1);
-      const int ox = px * p.out_sx + (t.phase & 1);
-      const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
-      const int64_t base = pix * p.ldc + static_cast<int64_t>(t.nt) * BN;
-
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>((acc * MB + mb) * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
-
-      const int ncols = min(BN, p.n_total - t.nt * BN);  // N tail: columns >= ncols are padding
-#pragma unroll 1
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      for (int it = part; it < total_it; it += kParts) {
+        const int mb = (MB == 1) ? 0 : (it >= nchunks ? 1 : 0);
+        const int c0 = (it - mb * nchunks) << 5;
+        const bool valid = (MB == 1) ? valid_mb[0] : (mb ? valid_mb[1] : valid_mb[0]);
+        const int64_t base = (MB == 1) ? base_mb[0] : (mb ? base_mb[1] : base_mb[0]);
         uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_32x32b_x32(tlane + static_cast<uint32_t>(mb * BN + c0), r);
+        uint4 rcur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+        if (it + kParts < total_it) issue_residual(it + kParts);
         tmem_ld_wait();
         const int nvec = min(4, (ncols - c0) >> 3);  // valid 8-channel vectors in this chunk
         float v[32];
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + t.nt * BN + c0);
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = (j < 2 * nvec) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b = b4[j];
             v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
             v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
             v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
-        if (p.residual != nullptr && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + base + c0);
+        if (has_res && valid) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (j < nvec) {
-              const uint4 u = __ldg(rp + j);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[j]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = __half22float2(h2[e]);
@@ -291,7 +339,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
         }
         if (do_stats) {
-          float* dst = s_stats + quarter * (BN / 2) + 2 * (c0 >> p.cpg_log2);
+          float* dst = s_stats + ew * (BN / 2) + 2 * (c0 >> p.cpg_log2);
           if (p.cpg_log2 == 2) chunk_group_stats<8>(v, valid, lane, dst);
           else if (p.cpg_log2 == 3) chunk_group_stats<4>(v, valid, lane, dst);
           else chunk_group_stats<2>(v, valid, lane, dst);
@@ -317,8 +365,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               if (j < 2 * nvec) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         }
-      }
-      }  // mb
+      }  // chunk loop
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -326,17 +373,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       if (acc == 0) acc_phase ^= 1u;
 
       if (do_stats) {
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         const int groups_in_tile = BN >> p.cpg_log2;
         if (et < 2 * groups_in_tile) {
           const int g = ((t.nt * BN) >> p.cpg_log2) + (et >> 1);
-          // fixed-order fold of the four warps' partials, then one fp64 reduction per (group, moment)
-          const float tot = ((s_stats[et] + s_stats[BN / 2 + et]) + s_stats[BN + et]) + s_stats[3 * (BN / 2) + et];
+          // fixed-order fold of the epilogue warps' partials, then one fp64 reduction per (group, moment)
+          float tot = 0.f;
+#pragma unroll
+          for (int wi = 0; wi < kEpiWarps; ++wi) {
+            tot += s_stats[wi * (BN / 2) + et];
+            s_stats[wi * (BN / 2) + et] = 0.f;
+          }
           atomicAdd(&p.stats[(static_cast<int64_t>(t.frame) * p.groups_total + g) * 2 + (et & 1)],
                     static_cast<double>(tot));
-          s_stats[et] = s_stats[BN / 2 + et] = s_stats[BN + et] = s_stats[3 * (BN / 2) + et] = 0.f;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
       }
     }
   }
@@ -366,7 +417,7 @@ struct ConvCfg<128> {  // N = 128: two 128-pixel blocks per tile so A+B bytes pe
 template <int BN>
 constexpr size_t conv_smem_bytes() {
   return 1024 /*align slack*/ + ConvCfg<BN>::kStages * (ConvCfg<BN>::kMB * kABytes + BN * kBlockK * 2) + (2 * ConvCfg<BN>::kStages + 4) * 8 +
-         16 + 4 * (BN / 2) * 4 + 64;
+         16 + kEpiWarps * (BN / 2) * 4 + BN * 4 + 64;
 }
 
 }  // namespace wfk
