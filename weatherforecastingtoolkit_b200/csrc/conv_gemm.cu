@@ -1,23 +1,28 @@
 // Implicit-GEMM convolution / GEMM for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
 //
-// Data layout: activations NHWC fp16 (channels innermost) so that a tile of 128 output pixels x 64
+// Data layout: activations NHWC fp16 (channels innermost) so that a block of 128 output pixels x 64
 // input channels is a TMA box (64, BW, 1, BH, 1) of the 5-D view (k, x, q, y, frame); TMA writes it
 // as 128 rows of 128 B with the 128-byte swizzle, which is exactly the K-major operand layout
 // tcgen05.mma reads. A 3x3 convolution is 9 "taps": the same box shifted by (dx, dy); rows that fall
 // outside the image are zero-filled by TMA, which implements the convolution's zero padding.
-// Weights are [slab][cout][cin] fp16 and arrive as the box (64, BN, 1) of the 3-D view (k, n, slab).
+// Weights are [slab][cout][cin] fp16 and arrive as the box (64, rows, 1) of the 3-D view (k, n, slab).
 //
-// Warp roles (192 threads, one persistent CTA per SM):
+// Warp roles (320 threads, one persistent CTA per SM):
 //   warp 0      : TMA producer (one elected lane)       -- fills the STAGES-deep smem ring
 //   warp 1      : TMEM allocator + MMA issuer (one lane) -- 4 x tcgen05.mma (K=16) per 64-wide K block
-//   warps 2..5  : epilogue -- tcgen05.ld the 128 x BN fp32 accumulator, + bias (+ residual),
-//                 GroupNorm sum / sum-of-squares of the result, fp16 / fp32 stores
-// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
-// the MMAs of tile i+1.
+//   warps 2..9  : epilogue -- tcgen05.ld the fp32 accumulator, + bias (+ residual), GroupNorm
+//                 sum / sum-of-squares of the result, fp16 / fp32 stores (two warps per TMEM lane quarter)
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Tile shapes: BN=256: one 128-pixel block per CTA; BN=128: MB=2 pixel blocks per CTA share the weight
+// tile. PAIR=true runs the kernel as 2-CTA clusters with tcgen05.mma.cta_group::2 (M=256 across the
+// pair): each CTA stages its own pixel blocks and only HALF of the weight tile, which cuts the shared
+// memory traffic per MAC by a third -- the limiter of the single-CTA kernel.
 //
 // Replaces (reference, all cuDNN / cuBLAS library calls): nn.Conv2d 3x3 / 1x1
 // (pipeline/models/autoencoderkl/resnet.py:405,421,452), Downsample2D (resnet.py:181-190),
 // Upsample2D (resnet.py:108-143), the attention linears and bmm's (attention.py:146-176).
+#include <cstdlib>
 #include <new>
 
 #include "internal.h"
@@ -26,8 +31,8 @@
 namespace wfk {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;   // fp16 elements = one 128 B swizzle row
-constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter: latency hiding by TLP
+constexpr int kBlockK = 64;  // fp16 elements = one 128 B swizzle row
+constexpr int kEpiWarps = 8;  // two per TMEM lane quarter: latency hiding by TLP
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kConvThreads = 64 + kEpiThreads;
 constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -37,6 +42,7 @@ struct ConvKernelParams {
   CUtensorMap b_map[2];
   int n_frames, tile_h, tile_w, tiles_x, tiles_y, tiles_n, n_total;
   int bw_log2;
+  int stack_x;  // pixel blocks of one tile are laid along x (GEMM-like, one row) instead of y
   int num_phases, taps_per_phase;
   int a_frame_mul, b_frame_mul;
   const float* bias;
@@ -115,10 +121,13 @@ __device__ __forceinline__ void chunk_group_stats(const float (&v)[32], bool val
   }
 }
 
-template <int BN, int MB, int STAGES>
+template <int BN, int MB, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  constexpr int kBBytes = BN * kBlockK * 2;
-  constexpr int kStageBytes = MB * kABytes + kBBytes;  // MB pixel blocks (128 rows each) share one weight tile
+  constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
+  constexpr int kBBytes = kBRows * kBlockK * 2;
+  constexpr int kStageBytes = MB * kABytes + kBBytes;
+  constexpr int kCtas = PAIR ? 2 : 1;
+  constexpr int kBlocksPerTile = MB * kCtas;       // 128-pixel blocks per (pair-)tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
@@ -127,19 +136,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [kEpiWarps][BN/4 groups max][2]
-  float* s_bias = s_stats + kEpiWarps * (BN / 2);                     // [BN] bias of the current N tile
+  float* s_bias = s_stats + kEpiWarps * (BN / 2);            // [BN] bias of the current N tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], 1);       // PAIR: only the leader arrives (expect_tx of BOTH CTAs' bytes)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&tempty_bar[i], kCtas * kEpiWarps);  // one arrive per epilogue warp (PAIR: of both CTAs)
     }
     fence_barrier_init();
   }
@@ -147,13 +158,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     tma_prefetch_desc(&p.a_map[0]);
     tma_prefetch_desc(&p.b_map[0]);
   }
-  if (warp == 1) tmem_alloc<2 * MB * BN>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm<2 * MB * BN>(tmem_slot);
+    else tmem_alloc<2 * MB * BN>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   const int total_tiles = p.num_phases * p.n_frames * p.tiles_y * p.tiles_x * p.tiles_n;
+  const int tile0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int bw = 1 << p.bw_log2;
   const int bh = kBlockM >> p.bw_log2;
 
@@ -162,9 +179,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
-        const int x0 = t.tx * bw, y0 = t.ty * bh * MB;
+        // first pixel block of this CTA inside the tile
+        const int blk0 = static_cast<int>(cta_rank) * MB;
+        const int bx0 = p.stack_x ? t.tx * kBlocksPerTile + blk0 : t.tx;
+        const int by0 = p.stack_x ? t.ty : t.ty * kBlocksPerTile + blk0;
         for (int ti = 0; ti < p.taps_per_phase; ++ti) {
           const wfk_tap tap = p.taps[t.phase * p.taps_per_phase + ti];
           const CUtensorMap* am = &p.a_map[tap.src];
@@ -172,13 +192,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           for (int kb = 0; kb < tap.kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = smem + stage * kStageBytes;
-            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            if (PAIR) {
+              // The peer's bytes complete_tx on the leader's barrier too; the peer itself never arrives (a
+              // release.cluster arrive per K block costs a fence on the producer's critical path). A peer
+              // running ahead only drives the tx-count negative until the leader's expect_tx lands.
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            }
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb)
-              tma_load_5d(sa + mb * kABytes, am, &full_bar[stage], tap.c_off + kb * kBlockK, x0 + tap.dx, tap.q,
-                          y0 + mb * bh + tap.dy, t.frame * p.a_frame_mul);
-            tma_load_3d(sa + MB * kABytes, bm, &full_bar[stage], kb * kBlockK, t.nt * BN,
-                        tap.b_slab + t.frame * p.b_frame_mul);
+            for (int mb = 0; mb < MB; ++mb) {
+              const int x0 = (p.stack_x ? bx0 + mb : bx0) * bw;
+              const int y0 = (p.stack_x ? by0 : by0 + mb) * bh;
+              if (PAIR)
+                tma_load_5d_2sm(sa + mb * kABytes, am, &full_bar[stage], tap.c_off + kb * kBlockK, x0 + tap.dx, tap.q,
+                                y0 + tap.dy, t.frame * p.a_frame_mul);
+              else
+                tma_load_5d(sa + mb * kABytes, am, &full_bar[stage], tap.c_off + kb * kBlockK, x0 + tap.dx, tap.q,
+                            y0 + tap.dy, t.frame * p.a_frame_mul);
+            }
+            if (PAIR)
+              tma_load_3d_2sm(sa + MB * kABytes, bm, &full_bar[stage], kb * kBlockK,
+                              t.nt * BN + static_cast<int>(cta_rank) * kBRows, tap.b_slab + t.frame * p.b_frame_mul);
+            else
+              tma_load_3d(sa + MB * kABytes, bm, &full_bar[stage], kb * kBlockK, t.nt * BN,
+                          tap.b_slab + t.frame * p.b_frame_mul);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -188,8 +226,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
+    if (lane == 0 && leader) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only when PAIR)
       // The issue loop must sustain one tcgen05.mma per 64 tensor-core cycles (N = 128), so descriptors
       // are built incrementally: the high word (SBO, version, swizzle) is constant, the low word is the
       // stage's start address >> 4 plus (bytes >> 4) per K slice / pixel block.
@@ -201,7 +239,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
       const uint32_t lo0 = static_cast<uint32_t>(desc0);
       const uint32_t idesc = p.idesc;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
         int kb_total = 0;
         for (int ti = 0; ti < p.taps_per_phase; ++ti) kb_total += p.taps[t.phase * p.taps_per_phase + ti].kblocks;
@@ -219,37 +257,45 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
-              const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + static_cast<uint32_t>(mb * (kABytes >> 4) + 2 * k));
-              umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
+              const uint64_t adesc =
+                  (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + static_cast<uint32_t>(mb * (kABytes >> 4) + 2 * k));
+              if (PAIR) umma_f16_2sm(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
+              else umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
             }
-            accumulate = 1;  // after BOTH pixel blocks have issued their first (overwriting) MMA
+            accumulate = 1;  // after EVERY pixel block has issued its first (overwriting) MMA
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs when PAIR) once these MMAs have read it
+          if (PAIR) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue(s)
+        if (PAIR) umma_commit_2sm(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else {
-    // -------------------------------------------------------------- epilogue (warps 2..5)
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;       // 0..kEpiThreads-1
-    const int ew = warp - 2;               // epilogue warp index: owns chunks ew/4, ew/4 + 2, ...
-    const int part = ew >> 2;
+    // -------------------------------------------------------------- epilogue (warps 2..9)
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;  // 0..kEpiThreads-1
+    const int ew = warp - 2;          // epilogue warp index
+    const int part = ew >> 2;         // which half of the chunk list this warp owns
+    constexpr int kParts = kEpiWarps / 4;
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool do_stats = p.stats != nullptr;
+    const bool has_res = p.residual != nullptr;
     int bias_nt = -1;
     if (do_stats) {
       for (int i = et; i < kEpiWarps * (BN / 2); i += kEpiThreads) s_stats[i] = 0.f;
       named_bar_sync(1, kEpiThreads);
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord t = decode_tile(p, tile);
       const int row = quarter * 32 + lane;
       if (t.nt != bias_nt) {  // stage this N tile's bias once (smem broadcast reads in the chunk loop)
@@ -261,13 +307,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         named_bar_sync(2, kEpiThreads);
         bias_nt = t.nt;
       }
-      // output coordinates of this thread's row in each of the MB pixel blocks
+      // output coordinates of this thread's row in each of this CTA's MB pixel blocks
       bool valid_mb[2] = {false, false};
       int64_t base_mb[2] = {0, 0};
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
-        const int py = (t.ty * MB + mb) * bh + (row >> p.bw_log2);
-        const int px = t.tx * bw + (row & (bw - 1));
+        const int blk = static_cast<int>(cta_rank) * MB + mb;
+        const int bx = p.stack_x ? t.tx * kBlocksPerTile + blk : t.tx;
+        const int by = p.stack_x ? t.ty : t.ty * kBlocksPerTile + blk;
+        const int py = by * bh + (row >> p.bw_log2);
+        const int px = bx * bw + (row & (bw - 1));
         valid_mb[mb] = (py < p.tile_h) && (px < p.tile_w);
         const int oy = py * p.out_sy + (t.phase >> 1);
         const int ox = px * p.out_sx + (t.phase & 1);
@@ -277,7 +326,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int ncols = min(BN, p.n_total - t.nt * BN);  // N tail: columns >= ncols are padding
       const int nchunks = (ncols + 31) >> 5;
       const int total_it = MB * nchunks;
-      const bool has_res = p.residual != nullptr;
       // residual values are prefetched one chunk ahead (and before the accumulator is even ready) so
       // their global-memory latency is off the epilogue's critical path
       uint4 rnext[4];
@@ -293,11 +341,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             if (c0_i + 8 * j < ncols) rnext[j] = __ldg(rp + j);
         }
       };
-      constexpr int kParts = kEpiWarps / 4;
       if (part < total_it) issue_residual(part);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * MB * BN);
+      const uint32_t tlane =
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * MB * BN);
 #pragma unroll 1
       for (int it = part; it < total_it; it += kParts) {
         const int mb = (MB == 1) ? 0 : (it >= nchunks ? 1 : 0);
@@ -366,9 +414,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
         }
       }  // chunk loop
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      // accumulator drained: hand the TMEM buffer back to the MMA warp (of the leader CTA when PAIR)
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
 
@@ -393,31 +445,93 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its smem
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * MB * BN>(tmem_base);
+    if (PAIR) tmem_dealloc_2sm<2 * MB * BN>(tmem_base);
+    else tmem_dealloc<2 * MB * BN>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------- host
-template <int BN>
+template <int BN, bool PAIR>
 struct ConvCfg;
 template <>
-struct ConvCfg<256> {
-  static constexpr int kStages = 4;
-  static constexpr int kMB = 1;
+struct ConvCfg<256, false> {
+  static constexpr int kMB = 1, kStages = 4;   // 48 KB / stage
 };
 template <>
-struct ConvCfg<128> {  // N = 128: two 128-pixel blocks per tile so A+B bytes per MAC match the 128x256 tile
-  static constexpr int kStages = 4;
-  static constexpr int kMB = 2;
+struct ConvCfg<128, false> {                   // two pixel blocks share the weight tile
+  static constexpr int kMB = 2, kStages = 4;   // 48 KB / stage
+};
+template <>
+struct ConvCfg<256, true> {
+  static constexpr int kMB = 1, kStages = 6;   // 16 + 16 KB / stage
+};
+template <>
+struct ConvCfg<128, true> {
+  static constexpr int kMB = 2, kStages = 5;   // 32 + 8 KB / stage
 };
 
-template <int BN>
+template <int BN, bool PAIR>
 constexpr size_t conv_smem_bytes() {
-  return 1024 /*align slack*/ + ConvCfg<BN>::kStages * (ConvCfg<BN>::kMB * kABytes + BN * kBlockK * 2) + (2 * ConvCfg<BN>::kStages + 4) * 8 +
-         16 + kEpiWarps * (BN / 2) * 4 + BN * 4 + 64;
+  return 1024 /*align slack*/ +
+         ConvCfg<BN, PAIR>::kStages * (ConvCfg<BN, PAIR>::kMB * kABytes + (PAIR ? BN / 2 : BN) * kBlockK * 2) +
+         (2 * ConvCfg<BN, PAIR>::kStages + 4) * 8 + 16 + kEpiWarps * (BN / 2) * 4 + BN * 4 + 64;
+}
+
+template <int BN, bool PAIR>
+cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s) {
+  using Cfg = ConvCfg<BN, PAIR>;
+  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(conv_smem_bytes<BN, PAIR>()));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = conv_smem_bytes<BN, PAIR>();
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, params);
+}
+
+// Largest number of co-resident 2-CTA clusters for the pair kernels (a persistent grid must not exceed it,
+// or the surplus clusters run as a second wave). Queried once per variant.
+template <int BN>
+int max_active_pairs() {
+  using Cfg = ConvCfg<BN, true>;
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, true>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(conv_smem_bytes<BN, true>()));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g_num_sms);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = conv_smem_bytes<BN, true>();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = g_num_sms / 2;
+  if (std::getenv("WFK_DEBUG")) fprintf(stderr, "[wfk] conv_gemm<%d,pair>: max active clusters = %d\n", BN, n);
+  cached = n;
+  return n;
 }
 
 }  // namespace wfk
@@ -425,6 +539,7 @@ constexpr size_t conv_smem_bytes() {
 struct wfk_conv_plan {
   wfk::ConvKernelParams params;
   int bn;
+  int pair;
   int grid;
 };
 
@@ -451,9 +566,9 @@ int encode_a(const wfk_view5& v, int bw, int bh, bool bf16, CUtensorMap* out) {
   return WFK_OK;
 }
 
-int encode_b(const wfk_view3& v, int bn, bool bf16, CUtensorMap* out) {
+int encode_b(const wfk_view3& v, int rows, bool bf16, CUtensorMap* out) {
   cuuint64_t dims[3], strides[2];
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(wfk::kBlockK), static_cast<cuuint32_t>(bn), 1u};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(wfk::kBlockK), static_cast<cuuint32_t>(rows), 1u};
   cuuint32_t estr[3] = {1, 1, 1};
   for (int i = 0; i < 3; ++i) dims[i] = static_cast<cuuint64_t>(v.dim[i]);
   for (int i = 1; i < 3; ++i) strides[i - 1] = static_cast<cuuint64_t>(v.stride[i]);
@@ -472,6 +587,15 @@ int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
   return ((1 << l) == v) ? l : -1;
+}
+
+bool pair_mode_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("WFK_CONV_PAIR");
+    mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return mode == 1;
 }
 
 }  // namespace
@@ -505,31 +629,37 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   WFK_REQUIRE(plan != nullptr, "out of memory");
   wfk::ConvKernelParams& p = plan->params;
   plan->bn = (d->n_total % 256 == 0 || d->n_total > 256) ? 256 : 128;
+  plan->pair = (pair_mode_enabled() && wfk::g_num_sms % 2 == 0) ? 1 : 0;
   if (d->stats != nullptr && d->n_total % plan->bn != 0) {
     delete plan;
     return wfk::fail(WFK_ERR_INVALID, "stats need n_total (%d) to be a multiple of the N tile (%d)", d->n_total, plan->bn);
   }
 
-  const int mb_blocks = plan->bn == 256 ? wfk::ConvCfg<256>::kMB : wfk::ConvCfg<128>::kMB;
-  // tile geometry: BW x BH = 128 output pixels, BW a power of two; minimise the padded area
+  // 128-pixel blocks per tile: MB per CTA, x2 for a CTA pair
+  const int mb_blocks = (plan->bn == 256 ? 1 : 2) * (plan->pair ? 2 : 1);
+  // GEMM-like problems (one row of pixels) stack a tile's blocks along x, images along y
+  const int stack_x = (d->tile_h == 1) ? 1 : 0;
+  // block geometry: BW x BH = 128 output pixels, BW a power of two; minimise the padded area
   int best_log2 = 7;
   long best_area = -1;
   for (int l = 7; l >= 3; --l) {
     const int bw = 1 << l, bh = 128 >> l;
-    const int bhe = bh * mb_blocks;
-    const long area = static_cast<long>((d->tile_w + bw - 1) / bw) * bw * (static_cast<long>((d->tile_h + bhe - 1) / bhe) * bhe);
+    const int ew = stack_x ? bw * mb_blocks : bw, eh = stack_x ? bh : bh * mb_blocks;
+    const long area = static_cast<long>((d->tile_w + ew - 1) / ew) * ew * (static_cast<long>((d->tile_h + eh - 1) / eh) * eh);
     if (best_area < 0 || area < best_area) {
       best_area = area;
       best_log2 = l;
     }
   }
   const int bw = 1 << best_log2, bh = 128 >> best_log2;
+  const int ew = stack_x ? bw * mb_blocks : bw, eh = stack_x ? bh : bh * mb_blocks;
   p.bw_log2 = best_log2;
+  p.stack_x = stack_x;
   p.n_frames = d->n_frames;
   p.tile_h = d->tile_h;
   p.tile_w = d->tile_w;
-  p.tiles_x = (d->tile_w + bw - 1) / bw;
-  p.tiles_y = (d->tile_h + bh * mb_blocks - 1) / (bh * mb_blocks);
+  p.tiles_x = (d->tile_w + ew - 1) / ew;
+  p.tiles_y = (d->tile_h + eh - 1) / eh;
   p.tiles_n = (d->n_total + plan->bn - 1) / plan->bn;
   p.n_total = d->n_total;
   p.num_phases = d->num_phases;
@@ -548,14 +678,15 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.ldc = d->ldc;
   p.cpg_log2 = cpg_log2;
   p.groups_total = d->stats ? (d->n_total >> cpg_log2) : 0;
-  p.idesc = wfk::umma_idesc_f16(128, static_cast<uint32_t>(plan->bn), d->operand_bf16 ? 1u : 0u);
+  p.idesc = wfk::umma_idesc_f16(plan->pair ? 256u : 128u, static_cast<uint32_t>(plan->bn), d->operand_bf16 ? 1u : 0u);
   for (int i = 0; i < WFK_MAX_TAPS; ++i) p.taps[i] = d->taps[i];
 
+  const int b_rows = plan->pair ? plan->bn / 2 : plan->bn;
   int rc = encode_a(d->a[0], bw, bh, d->operand_bf16 != 0, &p.a_map[0]);
-  if (rc == WFK_OK) rc = encode_b(d->b[0], plan->bn, d->operand_bf16 != 0, &p.b_map[0]);
+  if (rc == WFK_OK) rc = encode_b(d->b[0], b_rows, d->operand_bf16 != 0, &p.b_map[0]);
   if (rc == WFK_OK && uses_src1) {
     rc = encode_a(d->a[1], bw, bh, d->operand_bf16 != 0, &p.a_map[1]);
-    if (rc == WFK_OK) rc = encode_b(d->b[1], plan->bn, d->operand_bf16 != 0, &p.b_map[1]);
+    if (rc == WFK_OK) rc = encode_b(d->b[1], b_rows, d->operand_bf16 != 0, &p.b_map[1]);
   } else if (rc == WFK_OK) {
     p.a_map[1] = p.a_map[0];
     p.b_map[1] = p.b_map[0];
@@ -565,11 +696,16 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
     return rc;
   }
   const long total_tiles = static_cast<long>(p.num_phases) * p.n_frames * p.tiles_y * p.tiles_x * p.tiles_n;
-  if (total_tiles > 0x7fffffffL) {
+  if (total_tiles > 0x3fffffffL) {
     delete plan;
     return wfk::fail(WFK_ERR_INVALID, "too many tiles");
   }
-  plan->grid = static_cast<int>(total_tiles < wfk::g_num_sms ? total_tiles : wfk::g_num_sms);
+  if (plan->pair) {
+    const long pairs = plan->bn == 256 ? wfk::max_active_pairs<256>() : wfk::max_active_pairs<128>();
+    plan->grid = static_cast<int>(2 * (total_tiles < pairs ? total_tiles : pairs));
+  } else {
+    plan->grid = static_cast<int>(total_tiles < wfk::g_num_sms ? total_tiles : wfk::g_num_sms);
+  }
   *out = plan;
   return WFK_OK;
 }
@@ -578,24 +714,17 @@ extern "C" int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream) {
   WFK_REQUIRE_INIT();
   WFK_REQUIRE(plan != nullptr, "null plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv_gemm_kernel<256, wfk::ConvCfg<256>::kMB, wfk::ConvCfg<256>::kStages>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(wfk::conv_smem_bytes<256>())));
-    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv_gemm_kernel<128, wfk::ConvCfg<128>::kMB, wfk::ConvCfg<128>::kStages>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(wfk::conv_smem_bytes<128>())));
-    attr_set = true;
-  }
-  if (plan->bn == 256) {
-    wfk::conv_gemm_kernel<256, wfk::ConvCfg<256>::kMB, wfk::ConvCfg<256>::kStages>
-        <<<plan->grid, wfk::kConvThreads, wfk::conv_smem_bytes<256>(), s>>>(plan->params);
+  cudaError_t e;
+  if (plan->pair) {
+    e = (plan->bn == 256) ? wfk::launch_conv<256, true>(plan->params, plan->grid, s)
+                          : wfk::launch_conv<128, true>(plan->params, plan->grid, s);
   } else {
-    wfk::conv_gemm_kernel<128, wfk::ConvCfg<128>::kMB, wfk::ConvCfg<128>::kStages>
-        <<<plan->grid, wfk::kConvThreads, wfk::conv_smem_bytes<128>(), s>>>(plan->params);
+    e = (plan->bn == 256) ? wfk::launch_conv<256, false>(plan->params, plan->grid, s)
+                          : wfk::launch_conv<128, false>(plan->params, plan->grid, s);
   }
-  return wfk::launched("conv_gemm_kernel");
+  wfk::g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return wfk::fail(WFK_ERR_CUDA, "launch of conv_gemm_kernel failed: %s", cudaGetErrorString(e));
+  return WFK_OK;
 }
 
 extern "C" void wfk_conv_plan_destroy(wfk_conv_plan* plan) { delete plan; }
