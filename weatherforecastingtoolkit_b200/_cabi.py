@@ -102,7 +102,7 @@ def load() -> C.CDLL:
                 f"{_LIB_PATH} is missing: build it with `python -m weatherforecastingtoolkit_b200.build` "
                 "(there is no CPU / PyTorch fallback for this path)")
         lib = C.CDLL(os.fspath(_LIB_PATH))
-        for name, (res, args) in _PROTOTYPES.items():
+        for name, (res, args) in _PROTOTYPES.items():  # debug probes (wfk_debug_*) are bound ad hoc by scripts/
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args

@@ -34,8 +34,15 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = one 128 B swizzle row
 constexpr int kEpiWarps = 8;  // two per TMEM lane quarter: latency hiding by TLP
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kConvThreads = 64 + kEpiThreads;
+constexpr int kConvThreadsPlain = 64 + kEpiThreads;   // warps: TMA, MMA, 8 epilogue
+constexpr int kConvThreadsHalo = 96 + kEpiThreads;    // warps: TMA(A), MMA, TMA(B), 8 epilogue
 constexpr int kABytes = kBlockM * kBlockK * 2;
+// HALO mode (3x3 stride-1 taps): pixel blocks are 8 wide x 16 tall; ONE (8*MB+2) x 18 pixel halo box per
+// 64-channel K block serves all taps through shifted A descriptors (tcgen05's 128B swizzle is a pure
+// function of the shared-memory address -- probed in csrc/debug_mma.cu), so activations are staged once
+// instead of once per tap and the weight tiles stream through their own ring.
+constexpr int kHaloRows = 18;
+constexpr int kHaloBStages = 8;
 
 struct ConvKernelParams {
   CUtensorMap a_map[2];
@@ -43,6 +50,8 @@ struct ConvKernelParams {
   int n_frames, tile_h, tile_w, tiles_x, tiles_y, tiles_n, n_total;
   int bw_log2;
   int stack_x;  // pixel blocks of one tile are laid along x (GEMM-like, one row) instead of y
+  int seg_kblocks[2];  // HALO: K blocks of source 0 (all taps) and of source 1 (fused 1x1 shortcut, centre tap)
+  int seg1_slab;       // HALO: weight slab of the shortcut
   int num_phases, taps_per_phase;
   int a_frame_mul, b_frame_mul;
   const float* bias;
@@ -121,18 +130,28 @@ __device__ __forceinline__ void chunk_group_stats(const float (&v)[32], bool val
   }
 }
 
-template <int BN, int MB, int STAGES, bool PAIR>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+template <int BN, int MB, int STAGES, bool PAIR, bool HALO>
+__global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1)
+    conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
   constexpr int kBBytes = kBRows * kBlockK * 2;
-  constexpr int kStageBytes = MB * kABytes + kBBytes;
   constexpr int kCtas = PAIR ? 2 : 1;
   constexpr int kBlocksPerTile = MB * kCtas;       // 128-pixel blocks per (pair-)tile
+  // HALO: A ring of STAGES halo boxes + B ring of kHaloBStages weight tiles; else one ring of (A blocks + B)
+  constexpr int kHaloPitch = 8 * MB + 2;           // halo box width in pixels (= rows of 128 B per image row)
+  constexpr int kHaloBytes = kHaloPitch * kHaloRows * 128;
+  constexpr int kHaloStage = (kHaloBytes + 1023) & ~1023;
+  constexpr int kStageBytes = HALO ? kHaloStage : MB * kABytes + kBBytes;
+  constexpr int kBStages = HALO ? kHaloBStages : 0;
+  constexpr int kFirstEpiWarp = HALO ? 3 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint8_t* smem_b = smem + STAGES * kStageBytes;   // HALO only
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kBStages * kBBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* bfull_bar = empty_bar + STAGES;        // HALO only (kBStages each)
+  uint64_t* bempty_bar = bfull_bar + kBStages;
+  uint64_t* tfull_bar = bempty_bar + kBStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [kEpiWarps][BN/4 groups max][2]
@@ -147,6 +166,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);       // PAIR: only the leader arrives (expect_tx of BOTH CTAs' bytes)
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&bfull_bar[i], 1);
+      mbar_init(&bempty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -179,6 +202,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
+      if (HALO) {
+        // one halo box per (tile, source, 64-channel block): pixels [x0-1, x0+8*MB] x [y0-1, y0+16]
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+          const TileCoord t = decode_tile(p, tile);
+          const int x0 = (t.tx * kBlocksPerTile + static_cast<int>(cta_rank) * MB) * 8;
+          const int y0 = t.ty * 16;
+          for (int seg = 0; seg < 2; ++seg) {
+            const CUtensorMap* am = &p.a_map[seg];
+            for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              uint8_t* sa = smem + stage * kStageBytes;
+              if (PAIR) {
+                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kHaloBytes);
+                tma_load_5d_2sm(sa, am, &full_bar[stage], kb * kBlockK, x0 - 1, 0, y0 - 1, t.frame * p.a_frame_mul);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], kHaloBytes);
+                tma_load_5d(sa, am, &full_bar[stage], kb * kBlockK, x0 - 1, 0, y0 - 1, t.frame * p.a_frame_mul);
+              }
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      } else
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
         // first pixel block of this CTA inside the tile
@@ -239,6 +288,67 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
       const uint32_t lo0 = static_cast<uint32_t>(desc0);
       const uint32_t idesc = p.idesc;
+      if (HALO) {
+        // A descriptors: start = halo base + (r*pitch + 8*mb + s) rows, 8-row groups `pitch` rows apart
+        const uint32_t a_hi = (desc_hi & ~0x3FFFu) | static_cast<uint32_t>((kHaloPitch * 128) >> 4);
+        const uint32_t b_lo0 = lo0 + ((STAGES * kStageBytes) >> 4);
+        int bstage = 0;
+        uint32_t bphase = 0;
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+          const TileCoord t = decode_tile(p, tile);
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MB * BN);
+          uint32_t accumulate = 0;
+          for (int seg = 0; seg < 2; ++seg) {
+            const int ntaps = seg == 0 ? p.taps_per_phase : 1;
+            for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
+              for (int ti = 0; ti < ntaps; ++ti) {
+                int r = 1, sx = 1;
+                if (seg == 0) {
+                  const wfk_tap tap = p.taps[t.phase * p.taps_per_phase + ti];
+                  r = tap.dy + 1;
+                  sx = tap.dx + 1;
+                }
+                mbar_wait(&bfull_bar[bstage], bphase);
+                tc_fence_after();
+                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(bstage) * (kBBytes >> 4);
+                const uint32_t a_tap = a_lo + static_cast<uint32_t>((r * kHaloPitch + sx) * 8);  // rows * 128 B >> 4
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
+#pragma unroll
+                  for (int mb = 0; mb < MB; ++mb) {
+                    const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_tap + static_cast<uint32_t>(mb * 64 + 2 * k));
+                    if (PAIR) umma_f16_2sm(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
+                    else umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
+                  }
+                  accumulate = 1;
+                }
+                if (PAIR) umma_commit_2sm(&bempty_bar[bstage]);
+                else umma_commit(&bempty_bar[bstage]);
+                if (++bstage == kBStages) {
+                  bstage = 0;
+                  bphase ^= 1u;
+                }
+              }
+              if (PAIR) umma_commit_2sm(&empty_bar[stage]);
+              else umma_commit(&empty_bar[stage]);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+          if (PAIR) umma_commit_2sm(&tfull_bar[acc]);
+          else umma_commit(&tfull_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      } else
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
         int kb_total = 0;
@@ -279,11 +389,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         if (acc == 0) acc_phase ^= 1u;
       }
     }
+  } else if (HALO && warp == 2) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer for the weight tiles (HALO)
+      int bstage = 0;
+      uint32_t bphase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int seg = 0; seg < 2; ++seg) {
+          const CUtensorMap* bm = &p.b_map[seg];
+          const int ntaps = seg == 0 ? p.taps_per_phase : 1;
+          for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
+            for (int ti = 0; ti < ntaps; ++ti) {
+              const int slab = (seg == 0 ? p.taps[t.phase * p.taps_per_phase + ti].b_slab : p.seg1_slab) +
+                               t.frame * p.b_frame_mul;
+              mbar_wait(&bempty_bar[bstage], bphase ^ 1u);
+              uint8_t* sbt = smem_b + bstage * kBBytes;
+              if (PAIR) {
+                if (leader) mbar_arrive_expect_tx(&bfull_bar[bstage], 2 * kBBytes);
+                tma_load_3d_2sm(sbt, bm, &bfull_bar[bstage], kb * kBlockK,
+                                t.nt * BN + static_cast<int>(cta_rank) * kBRows, slab);
+              } else {
+                mbar_arrive_expect_tx(&bfull_bar[bstage], kBBytes);
+                tma_load_3d(sbt, bm, &bfull_bar[bstage], kb * kBlockK, t.nt * BN, slab);
+              }
+              if (++bstage == kBStages) {
+                bstage = 0;
+                bphase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
   } else {
-    // -------------------------------------------------------------- epilogue (warps 2..9)
+    // -------------------------------------------------------------- epilogue (8 warps)
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;  // 0..kEpiThreads-1
-    const int ew = warp - 2;          // epilogue warp index
+    const int et = threadIdx.x - 32 * kFirstEpiWarp;  // 0..kEpiThreads-1
+    const int ew = warp - kFirstEpiWarp;              // epilogue warp index
     const int part = ew >> 2;         // which half of the chunk list this warp owns
     constexpr int kParts = kEpiWarps / 4;
     int acc = 0;
@@ -455,47 +598,59 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------- host
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool HALO>
 struct ConvCfg;
 template <>
-struct ConvCfg<256, false> {
+struct ConvCfg<256, false, false> {
   static constexpr int kMB = 1, kStages = 4;   // 48 KB / stage
 };
 template <>
-struct ConvCfg<128, false> {                   // two pixel blocks share the weight tile
+struct ConvCfg<128, false, false> {            // two pixel blocks share the weight tile
   static constexpr int kMB = 2, kStages = 4;   // 48 KB / stage
 };
 template <>
-struct ConvCfg<256, true> {
+struct ConvCfg<256, true, false> {
   static constexpr int kMB = 1, kStages = 6;   // 16 + 16 KB / stage
 };
 template <>
-struct ConvCfg<128, true> {
+struct ConvCfg<128, true, false> {
   static constexpr int kMB = 2, kStages = 5;   // 32 + 8 KB / stage
 };
+template <>
+struct ConvCfg<256, true, true> {
+  static constexpr int kMB = 1, kStages = 3;   // 3 x 23 KB halo boxes + 8 x 16 KB weight tiles
+};
+template <>
+struct ConvCfg<128, true, true> {
+  static constexpr int kMB = 2, kStages = 3;   // 3 x 41 KB halo boxes + 8 x 8 KB weight tiles
+};
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool HALO>
 constexpr size_t conv_smem_bytes() {
-  return 1024 /*align slack*/ +
-         ConvCfg<BN, PAIR>::kStages * (ConvCfg<BN, PAIR>::kMB * kABytes + (PAIR ? BN / 2 : BN) * kBlockK * 2) +
-         (2 * ConvCfg<BN, PAIR>::kStages + 4) * 8 + 16 + kEpiWarps * (BN / 2) * 4 + BN * 4 + 64;
+  using Cfg = ConvCfg<BN, PAIR, HALO>;
+  constexpr size_t b_bytes = static_cast<size_t>(PAIR ? BN / 2 : BN) * kBlockK * 2;
+  constexpr size_t halo_stage = (static_cast<size_t>(8 * Cfg::kMB + 2) * kHaloRows * 128 + 1023) & ~static_cast<size_t>(1023);
+  constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + kHaloBStages * b_bytes
+                               : Cfg::kStages * (Cfg::kMB * kABytes + b_bytes);
+  return 1024 /*align slack*/ + ring + (2 * Cfg::kStages + 2 * kHaloBStages + 4) * 8 + 16 +
+         kEpiWarps * (BN / 2) * 4 + BN * 4 + 64;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool HALO>
 cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s) {
-  using Cfg = ConvCfg<BN, PAIR>;
-  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, PAIR>;
+  using Cfg = ConvCfg<BN, PAIR, HALO>;
+  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, PAIR, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(conv_smem_bytes<BN, PAIR>()));
+                                         static_cast<int>(conv_smem_bytes<BN, PAIR, HALO>()));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = conv_smem_bytes<BN, PAIR>();
+  cfg.blockDim = dim3(HALO ? kConvThreadsHalo : kConvThreadsPlain);
+  cfg.dynamicSmemBytes = conv_smem_bytes<BN, PAIR, HALO>();
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -509,17 +664,18 @@ cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s
 
 // Largest number of co-resident 2-CTA clusters for the pair kernels (a persistent grid must not exceed it,
 // or the surplus clusters run as a second wave). Queried once per variant.
-template <int BN>
+template <int BN, bool HALO>
 int max_active_pairs() {
-  using Cfg = ConvCfg<BN, true>;
+  using Cfg = ConvCfg<BN, true, HALO>;
   static int cached = -1;
   if (cached >= 0) return cached;
-  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, true>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(conv_smem_bytes<BN, true>()));
+  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, true, HALO>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>(conv_smem_bytes<BN, true, HALO>()));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(g_num_sms);
-  cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = conv_smem_bytes<BN, true>();
+  cfg.blockDim = dim3(HALO ? kConvThreadsHalo : kConvThreadsPlain);
+  cfg.dynamicSmemBytes = conv_smem_bytes<BN, true, HALO>();
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
@@ -529,7 +685,7 @@ int max_active_pairs() {
   cfg.numAttrs = 1;
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = g_num_sms / 2;
-  if (std::getenv("WFK_DEBUG")) fprintf(stderr, "[wfk] conv_gemm<%d,pair>: max active clusters = %d\n", BN, n);
+  if (std::getenv("WFK_DEBUG")) fprintf(stderr, "[wfk] conv_gemm<%d,pair,halo=%d>: max active clusters = %d\n", BN, (int)HALO, n);
   cached = n;
   return n;
 }
@@ -540,6 +696,7 @@ struct wfk_conv_plan {
   wfk::ConvKernelParams params;
   int bn;
   int pair;
+  int halo;
   int grid;
 };
 
@@ -587,6 +744,44 @@ int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
   return ((1 << l) == v) ? l : -1;
+}
+
+bool halo_mode_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("WFK_CONV_HALO");
+    mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return mode == 1;
+}
+
+// HALO applies to stride-1 taps within one pixel of the centre on a plain NHWC view (3x3 convolutions, the
+// 2x2 sub-pixel phases of the upsampler), optionally followed by ONE centre tap on source 1 (fused shortcut).
+bool halo_eligible(const wfk_conv_desc* d, int* n_src0_taps, int* kb0, int* kb1, int* slab1) {
+  if (d->tile_h < 2 || d->a[0].dim[2] != 1 || d->a_frame_mul != 1) return false;
+  if (d->a[0].dim[1] != d->tile_w || d->a[0].dim[3] != d->tile_h) return false;
+  const int tpp = d->taps_per_phase;
+  *kb1 = 0;
+  *slab1 = 0;
+  int n0 = tpp;
+  const wfk_tap& last = d->taps[tpp - 1];
+  if (last.src == 1) {
+    if (d->num_phases != 1 || last.dx != 0 || last.dy != 0 || last.q != 0 || last.c_off != 0) return false;
+    if (d->a[1].dim[2] != 1 || d->a[1].dim[1] != d->tile_w || d->a[1].dim[3] != d->tile_h) return false;
+    *kb1 = last.kblocks;
+    *slab1 = last.b_slab;
+    n0 = tpp - 1;
+  }
+  if (n0 < 1) return false;
+  *kb0 = d->taps[0].kblocks;
+  for (int ph = 0; ph < d->num_phases; ++ph)
+    for (int i = 0; i < n0; ++i) {
+      const wfk_tap& t = d->taps[ph * tpp + i];
+      if (t.src != 0 || t.q != 0 || t.c_off != 0 || t.dx < -1 || t.dx > 1 || t.dy < -1 || t.dy > 1 || t.kblocks != *kb0)
+        return false;
+    }
+  *n_src0_taps = n0;
+  return true;
 }
 
 bool pair_mode_enabled() {
@@ -637,12 +832,14 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
 
   // 128-pixel blocks per tile: MB per CTA, x2 for a CTA pair
   const int mb_blocks = (plan->bn == 256 ? 1 : 2) * (plan->pair ? 2 : 1);
+  int n_src0_taps = d->taps_per_phase, kb0 = 0, kb1 = 0, slab1 = 0;
+  plan->halo = (plan->pair && halo_mode_enabled() && halo_eligible(d, &n_src0_taps, &kb0, &kb1, &slab1)) ? 1 : 0;
   // GEMM-like problems (one row of pixels) stack a tile's blocks along x, images along y
-  const int stack_x = (d->tile_h == 1) ? 1 : 0;
+  const int stack_x = (d->tile_h == 1 || plan->halo) ? 1 : 0;
   // block geometry: BW x BH = 128 output pixels, BW a power of two; minimise the padded area
   int best_log2 = 7;
   long best_area = -1;
-  for (int l = 7; l >= 3; --l) {
+  for (int l = plan->halo ? 3 : 7; l >= 3; --l) {
     const int bw = 1 << l, bh = 128 >> l;
     const int ew = stack_x ? bw * mb_blocks : bw, eh = stack_x ? bh : bh * mb_blocks;
     const long area = static_cast<long>((d->tile_w + ew - 1) / ew) * ew * (static_cast<long>((d->tile_h + eh - 1) / eh) * eh);
@@ -663,7 +860,10 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.tiles_n = (d->n_total + plan->bn - 1) / plan->bn;
   p.n_total = d->n_total;
   p.num_phases = d->num_phases;
-  p.taps_per_phase = d->taps_per_phase;
+  p.taps_per_phase = plan->halo ? n_src0_taps : d->taps_per_phase;
+  p.seg_kblocks[0] = kb0;
+  p.seg_kblocks[1] = kb1;
+  p.seg1_slab = slab1;
   p.a_frame_mul = d->a_frame_mul;
   p.b_frame_mul = d->b_frame_mul;
   p.bias = d->bias;
@@ -680,12 +880,16 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.groups_total = d->stats ? (d->n_total >> cpg_log2) : 0;
   p.idesc = wfk::umma_idesc_f16(plan->pair ? 256u : 128u, static_cast<uint32_t>(plan->bn), d->operand_bf16 ? 1u : 0u);
   for (int i = 0; i < WFK_MAX_TAPS; ++i) p.taps[i] = d->taps[i];
+  if (plan->halo && n_src0_taps != d->taps_per_phase)  // drop the shortcut tap from the (single-phase) tap list
+    for (int i = 0; i < n_src0_taps; ++i) p.taps[i] = d->taps[i];
 
   const int b_rows = plan->pair ? plan->bn / 2 : plan->bn;
-  int rc = encode_a(d->a[0], bw, bh, d->operand_bf16 != 0, &p.a_map[0]);
+  const int mb_cta = plan->bn == 256 ? 1 : 2;
+  const int a_bw = plan->halo ? 8 * mb_cta + 2 : bw, a_bh = plan->halo ? wfk::kHaloRows : bh;
+  int rc = encode_a(d->a[0], a_bw, a_bh, d->operand_bf16 != 0, &p.a_map[0]);
   if (rc == WFK_OK) rc = encode_b(d->b[0], b_rows, d->operand_bf16 != 0, &p.b_map[0]);
   if (rc == WFK_OK && uses_src1) {
-    rc = encode_a(d->a[1], bw, bh, d->operand_bf16 != 0, &p.a_map[1]);
+    rc = encode_a(d->a[1], a_bw, a_bh, d->operand_bf16 != 0, &p.a_map[1]);
     if (rc == WFK_OK) rc = encode_b(d->b[1], b_rows, d->operand_bf16 != 0, &p.b_map[1]);
   } else if (rc == WFK_OK) {
     p.a_map[1] = p.a_map[0];
@@ -701,7 +905,8 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
     return wfk::fail(WFK_ERR_INVALID, "too many tiles");
   }
   if (plan->pair) {
-    const long pairs = plan->bn == 256 ? wfk::max_active_pairs<256>() : wfk::max_active_pairs<128>();
+    const long pairs = plan->halo ? (plan->bn == 256 ? wfk::max_active_pairs<256, true>() : wfk::max_active_pairs<128, true>())
+                                  : (plan->bn == 256 ? wfk::max_active_pairs<256, false>() : wfk::max_active_pairs<128, false>());
     plan->grid = static_cast<int>(2 * (total_tiles < pairs ? total_tiles : pairs));
   } else {
     plan->grid = static_cast<int>(total_tiles < wfk::g_num_sms ? total_tiles : wfk::g_num_sms);
@@ -715,12 +920,15 @@ extern "C" int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream) {
   WFK_REQUIRE(plan != nullptr, "null plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (plan->pair) {
-    e = (plan->bn == 256) ? wfk::launch_conv<256, true>(plan->params, plan->grid, s)
-                          : wfk::launch_conv<128, true>(plan->params, plan->grid, s);
+  if (plan->halo) {
+    e = (plan->bn == 256) ? wfk::launch_conv<256, true, true>(plan->params, plan->grid, s)
+                          : wfk::launch_conv<128, true, true>(plan->params, plan->grid, s);
+  } else if (plan->pair) {
+    e = (plan->bn == 256) ? wfk::launch_conv<256, true, false>(plan->params, plan->grid, s)
+                          : wfk::launch_conv<128, true, false>(plan->params, plan->grid, s);
   } else {
-    e = (plan->bn == 256) ? wfk::launch_conv<256, false>(plan->params, plan->grid, s)
-                          : wfk::launch_conv<128, false>(plan->params, plan->grid, s);
+    e = (plan->bn == 256) ? wfk::launch_conv<256, false, false>(plan->params, plan->grid, s)
+                          : wfk::launch_conv<128, false, false>(plan->params, plan->grid, s);
   }
   wfk::g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return wfk::fail(WFK_ERR_CUDA, "launch of conv_gemm_kernel failed: %s", cudaGetErrorString(e));
