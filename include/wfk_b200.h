@@ -153,6 +153,8 @@ typedef struct wfk_conv_desc {
   int32_t ldc;           /* output / residual channel pitch in elements                         */
   int32_t cpg;           /* channels per GroupNorm group (4, 8 or 16) when stats != NULL        */
   int32_t operand_bf16;  /* 0: fp16 operands (default), 1: bf16 operands                        */
+  const void* gn_table;  /* optional fused GroupNorm+SiLU on A source 0 (3x3 stride-1 convs only):
+                            [n_frames][cin] float2 (scale, shift) from wfk_gn_table, or NULL          */
 } wfk_conv_desc;
 
 typedef struct wfk_conv_plan wfk_conv_plan;
@@ -165,6 +167,11 @@ void wfk_conv_plan_destroy(wfk_conv_plan* plan);
  * stats: [n][groups][2] double (sum, sum of squares over the group's c/groups * hw values). */
 int wfk_groupnorm_apply(const void* x, const double* stats, const float* gamma, const float* beta, int n,
                         int hw, int c, int groups, float eps, int apply_silu, void* out, void* stream);
+
+/* Per-(frame, channel) scale/shift of a GroupNorm whose apply (+SiLU) is fused into the consuming
+ * convolution's operand staging: table[n][c] = (rstd*gamma, beta - mean*rstd*gamma). */
+int wfk_gn_table(const double* stats, const float* gamma, const float* beta, int n, int hw, int c, int groups,
+                 float eps, void* table, void* stream);
 
 /* Direct 3x3 (pad 1, stride 1) convolution for tiny input-channel counts.  Replaces
  * encoder.conv_in (vae.py:24) and post_quant_conv + decoder.conv_in (autoencoder_kl.py:87,

@@ -53,6 +53,7 @@ class ConvDesc(C.Structure):
         ("stats", C.c_void_p),
         ("out_rows", C.c_int32), ("out_cols", C.c_int32), ("out_sy", C.c_int32), ("out_sx", C.c_int32),
         ("ldc", C.c_int32), ("cpg", C.c_int32), ("operand_bf16", C.c_int32),
+        ("gn_table", C.c_void_p),
     ]
 
 
@@ -73,6 +74,8 @@ _PROTOTYPES = {
     "wfk_conv_plan_destroy": (None, [C.c_void_p]),
     "wfk_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "wfk_gn_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                               C.c_void_p, C.c_void_p]),
     "wfk_conv3x3_small_cin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "wfk_conv3x3_small_cout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

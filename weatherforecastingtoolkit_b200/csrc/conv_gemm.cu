@@ -35,7 +35,8 @@ constexpr int kBlockK = 64;  // fp16 elements = one 128 B swizzle row
 constexpr int kEpiWarps = 8;  // two per TMEM lane quarter: latency hiding by TLP
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kConvThreadsPlain = 64 + kEpiThreads;   // warps: TMA, MMA, 8 epilogue
-constexpr int kConvThreadsHalo = 96 + kEpiThreads;    // warps: TMA(A), MMA, TMA(B), 8 epilogue
+constexpr int kXformWarps = 4;                         // HALO: GroupNorm+SiLU applied in place to the staged halo
+constexpr int kConvThreadsHalo = 96 + 32 * kXformWarps + kEpiThreads;  // warps: TMA(A), MMA, TMA(B), 4 transform, 8 epilogue
 constexpr int kABytes = kBlockM * kBlockK * 2;
 // HALO mode (3x3 stride-1 taps): pixel blocks are 8 wide x 16 tall; ONE (8*MB+2) x 18 pixel halo box per
 // 64-channel K block serves all taps through shifted A descriptors (tcgen05's 128B swizzle is a pure
@@ -52,6 +53,8 @@ struct ConvKernelParams {
   int stack_x;  // pixel blocks of one tile are laid along x (GEMM-like, one row) instead of y
   int seg_kblocks[2];  // HALO: K blocks of source 0 (all taps) and of source 1 (fused 1x1 shortcut, centre tap)
   int seg1_slab;       // HALO: weight slab of the shortcut
+  const float2* gn_table;  // HALO: [frame][cin] (scale, shift) of a fused GroupNorm+SiLU on source 0, or null
+  int gn_cin;
   int num_phases, taps_per_phase;
   int a_frame_mul, b_frame_mul;
   const float* bias;
@@ -143,18 +146,19 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
   constexpr int kHaloStage = (kHaloBytes + 1023) & ~1023;
   constexpr int kStageBytes = HALO ? kHaloStage : MB * kABytes + kBBytes;
   constexpr int kBStages = HALO ? kHaloBStages : 0;
-  constexpr int kFirstEpiWarp = HALO ? 3 : 2;
+  constexpr int kFirstEpiWarp = HALO ? 3 + kXformWarps : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem + STAGES * kStageBytes;   // HALO only
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kBStages * kBBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* bfull_bar = empty_bar + STAGES;        // HALO only (kBStages each)
+  uint64_t* ready_bar = empty_bar + STAGES;        // HALO only: halo transformed (or passed through)
+  uint64_t* bfull_bar = ready_bar + (HALO ? STAGES : 0);  // HALO only (kBStages each)
   uint64_t* bempty_bar = bfull_bar + kBStages;
   uint64_t* tfull_bar = bempty_bar + kBStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [kEpiWarps][BN/4 groups max][2]
+  float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [kEpiWarps][BN/4 groups max][2], 16 B aligned (s_bias is read as float4)
   float* s_bias = s_stats + kEpiWarps * (BN / 2);            // [BN] bias of the current N tile
 
   const int warp = threadIdx.x >> 5;
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
       mbar_init(&full_bar[i], 1);       // PAIR: only the leader arrives (expect_tx of BOTH CTAs' bytes)
       mbar_init(&empty_bar[i], 1);
     }
+    if (HALO)
+      for (int i = 0; i < STAGES; ++i) mbar_init(&ready_bar[i], kCtas * kXformWarps);
     for (int i = 0; i < kBStages; ++i) {
       mbar_init(&bfull_bar[i], 1);
       mbar_init(&bempty_bar[i], 1);
@@ -213,13 +219,9 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
             for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               uint8_t* sa = smem + stage * kStageBytes;
-              if (PAIR) {
-                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kHaloBytes);
-                tma_load_5d_2sm(sa, am, &full_bar[stage], kb * kBlockK, x0 - 1, 0, y0 - 1, t.frame * p.a_frame_mul);
-              } else {
-                mbar_arrive_expect_tx(&full_bar[stage], kHaloBytes);
-                tma_load_5d(sa, am, &full_bar[stage], kb * kBlockK, x0 - 1, 0, y0 - 1, t.frame * p.a_frame_mul);
-              }
+              // each CTA's box completes on its OWN barrier: its transform warps consume it first
+              mbar_arrive_expect_tx(&full_bar[stage], kHaloBytes);
+              tma_load_5d(sa, am, &full_bar[stage], kb * kBlockK, x0 - 1, 0, y0 - 1, t.frame * p.a_frame_mul);
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
           for (int seg = 0; seg < 2; ++seg) {
             const int ntaps = seg == 0 ? p.taps_per_phase : 1;
             for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
-              mbar_wait(&full_bar[stage], phase);
+              mbar_wait(&ready_bar[stage], phase);
               tc_fence_after();
               const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
               for (int ti = 0; ti < ntaps; ++ti) {
@@ -418,6 +420,67 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
                 bphase ^= 1u;
               }
             }
+          }
+        }
+      }
+    }
+  } else if (HALO && warp < 3 + kXformWarps) {
+    // -------------------------------------------------------------- halo transform (HALO, warps 3..6)
+    // GroupNorm apply + SiLU of the consumer's input, fused: y = silu(a[c]*x + b[c]) in place on the staged
+    // halo (once per element, reused by all nine taps). Pixels outside the image stay the zeros TMA wrote
+    // (the convolution pads AFTER the activation). Without a table the halo is passed through unchanged.
+    const int xt = threadIdx.x - 96;      // 0..127
+    const int lc = xt & 7;                // logical 16-byte chunk (8 channels) this thread owns
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const TileCoord t = decode_tile(p, tile);
+      const int x0 = (t.tx * kBlocksPerTile + static_cast<int>(cta_rank) * MB) * 8 - 1;
+      const int y0 = t.ty * 16 - 1;
+      for (int seg = 0; seg < 2; ++seg) {
+        for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (seg == 0 && p.gn_table != nullptr) {
+            float ga[8], gb[8];
+            const float4* tp = reinterpret_cast<const float4*>(p.gn_table + static_cast<int64_t>(t.frame) * p.gn_cin +
+                                                               kb * kBlockK + lc * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 v = __ldg(tp + j);
+              ga[2 * j] = v.x;
+              gb[2 * j] = v.y;
+              ga[2 * j + 1] = v.z;
+              gb[2 * j + 1] = v.w;
+            }
+            uint8_t* sa = smem + stage * kStageBytes;
+            for (int row = xt >> 3; row < kHaloPitch * kHaloRows; row += (32 * kXformWarps) >> 3) {
+              const int hy = row / kHaloPitch, hx = row - hy * kHaloPitch;
+              const int py = y0 + hy, px = x0 + hx;
+              if (py < 0 || py >= p.tile_h || px < 0 || px >= p.tile_w) continue;
+              uint4* cp = reinterpret_cast<uint4*>(sa + row * 128 + ((lc ^ (row & 7)) << 4));
+              uint4 u = *cp;
+              __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(h2[e]);
+                f.x = fmaf(f.x, ga[2 * e], gb[2 * e]);
+                f.y = fmaf(f.y, ga[2 * e + 1], gb[2 * e + 1]);
+                f.x = __fdividef(f.x, 1.f + __expf(-f.x));
+                f.y = __fdividef(f.y, 1.f + __expf(-f.y));
+                h2[e] = __floats2half2_rn(f.x, f.y);
+              }
+              *cp = u;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to tcgen05.mma
+          }
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_leader(&ready_bar[stage]);
+            else mbar_arrive(&ready_bar[stage]);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -632,7 +695,7 @@ constexpr size_t conv_smem_bytes() {
   constexpr size_t halo_stage = (static_cast<size_t>(8 * Cfg::kMB + 2) * kHaloRows * 128 + 1023) & ~static_cast<size_t>(1023);
   constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + kHaloBStages * b_bytes
                                : Cfg::kStages * (Cfg::kMB * kABytes + b_bytes);
-  return 1024 /*align slack*/ + ring + (2 * Cfg::kStages + 2 * kHaloBStages + 4) * 8 + 16 +
+  return 1024 /*align slack*/ + ring + (3 * Cfg::kStages + 2 * kHaloBStages + 4) * 8 + 16 +
          kEpiWarps * (BN / 2) * 4 + BN * 4 + 64;
 }
 
@@ -864,6 +927,12 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.seg_kblocks[0] = kb0;
   p.seg_kblocks[1] = kb1;
   p.seg1_slab = slab1;
+  p.gn_table = static_cast<const float2*>(d->gn_table);
+  p.gn_cin = static_cast<int>(d->a[0].dim[0]);
+  if (d->gn_table != nullptr && !plan->halo) {
+    delete plan;
+    return wfk::fail(WFK_ERR_INVALID, "a fused GroupNorm+SiLU input (gn_table) needs a HALO-eligible 3x3 stride-1 convolution");
+  }
   p.a_frame_mul = d->a_frame_mul;
   p.b_frame_mul = d->b_frame_mul;
   p.bias = d->bias;

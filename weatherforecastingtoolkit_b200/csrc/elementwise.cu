@@ -118,6 +118,24 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   for (int i = threadIdx.x; i < cols; i += blockDim.x) dst[i] = __float2half_rn(s_row[i] * inv);
 }
 
+// (scale, shift) per (frame, channel) of a GroupNorm, for consumers that fuse the apply step.
+__global__ void gn_table_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int hw, int c, int groups, float eps,
+                                float2* __restrict__ table) {
+  const int n = blockIdx.x;
+  const int cpg = c / groups;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const int g = ch / cpg;
+    const double cnt = static_cast<double>(cpg) * hw;
+    const double mean = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 0] / cnt;
+    double var = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 1] / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = static_cast<float>(rsqrt(var + static_cast<double>(eps)));
+    const float a = rstd * gamma[ch];
+    table[static_cast<int64_t>(n) * c + ch] = make_float2(a, beta[ch] - static_cast<float>(mean) * a);
+  }
+}
+
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, int64_t n, __half* __restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2half_rn(in[i]);
@@ -139,6 +157,16 @@ extern "C" int wfk_groupnorm_apply(const void* x, const double* stats, const flo
   wfk::gn_apply_kernel<<<grid, 256, (2 * c + 2 * groups) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), stats, gamma, beta, hw, c, groups, eps, apply_silu, static_cast<__half*>(out), ppb);
   return wfk::launched("gn_apply_kernel");
+}
+
+extern "C" int wfk_gn_table(const double* stats, const float* gamma, const float* beta, int n, int hw, int c,
+                            int groups, float eps, void* table, void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(stats && gamma && beta && table, "null pointer");
+  WFK_REQUIRE(n > 0 && hw > 0 && c > 0 && groups > 0 && c % groups == 0, "bad shape");
+  wfk::gn_table_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats, gamma, beta, hw, c, groups, eps,
+                                                                        static_cast<float2*>(table));
+  return wfk::launched("gn_table_kernel");
 }
 
 extern "C" int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, void* stream) {

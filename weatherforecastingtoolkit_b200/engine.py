@@ -184,6 +184,10 @@ class AKLEngine:
         if self.in_ch > 4 or self.lc > 4 or self.out_ch not in (1, 2, 4, 8) or 2 * self.lc not in (2, 4, 8):
             raise ValueError("unsupported in/out/latent channel counts for the direct edge-conv kernels")
         self.w = PackedAKL(cfg, sd, self.device)
+        # fused GroupNorm needs the HALO conv path (CTA pairs); both can be switched off for A/B runs
+        import os
+        self.fuse_gn = (os.environ.get("WFK_FUSE_GN", "1") != "0" and os.environ.get("WFK_CONV_HALO", "1") != "0"
+                        and os.environ.get("WFK_CONV_PAIR", "1") != "0")
         self._plans: Dict[Tuple, "_Program"] = {}
         self._keep: List = []
 
@@ -303,9 +307,22 @@ class _Program:
         d.operand_bf16 = 0
 
     # ------------------------------------------------------------------ layer builders
+    def gn_table(self, x: _Act, pname: str, what="gn_table") -> torch.Tensor:
+        """(scale, shift) per (frame, channel) of GroupNorm(x): the apply + SiLU is fused into the consuming
+        3x3 convolution's operand staging instead of a separate read+write pass over the tensor."""
+        n, h, w, c = x.shape
+        tab = self.pool.get((n, c, 2), torch.float32)
+        t = self.eng.w.t
+        self._add(self.lib.wfk_gn_table,
+                  (x.stats.data_ptr(), t[pname + ".weight"].data_ptr(), t[pname + ".bias"].data_ptr(), n, h * w, c,
+                   self.eng.groups, GN_EPS, tab.data_ptr()), what)
+        return tab
+
     def conv3x3(self, x: _Act, wname: str, bias: torch.Tensor, cout: int, residual: Optional[torch.Tensor] = None,
-                shortcut: Optional[Tuple[torch.Tensor, str]] = None, want_stats=True, what="conv3x3") -> _Act:
-        """3x3 stride-1 pad-1 conv (+bias, +residual | fused 1x1 shortcut) -> new activation."""
+                shortcut: Optional[Tuple[torch.Tensor, str]] = None, want_stats=True, what="conv3x3",
+                gn_tab: Optional[torch.Tensor] = None) -> _Act:
+        """3x3 stride-1 pad-1 conv (+bias, +residual | fused 1x1 shortcut) -> new activation. With ``gn_tab`` the
+        input is the RAW tensor and GroupNorm+SiLU is applied while it is staged in shared memory."""
         n, h, w, cin = x.shape
         wt = self.eng.w.t[wname]
         out = self.pool.get((n, h, w, cout))
@@ -329,6 +346,7 @@ class _Program:
             d.taps_per_phase = 10
         d.a_frame_mul, d.b_frame_mul = 1, 0
         self._epilogue(d, bias, residual, out, None, stats, h, w, cout)
+        d.gn_table = _ptr(gn_tab)
         k_total = 9 * cin + (shortcut[0].shape[3] if shortcut is not None else 0)
         self._conv_plan(d, what, 2.0 * n * h * w * cout * k_total)
         return _Act(out, stats)
@@ -403,6 +421,22 @@ class _Program:
         t = self.eng.w.t
         cin = x.shape[3]
         cout = t[p + ".conv1.bias"].numel()
+        if self.eng.fuse_gn and x.shape[1] >= 2:
+            # GroupNorm apply + SiLU fused into the convs' halo staging: no normalised copies in HBM
+            t1 = self.gn_table(x, p + ".norm1", what=p + ".norm1(table)")
+            h1 = self.conv3x3(x, p + ".conv1.w", t[p + ".conv1.bias"], cout, what=p + ".gn1+conv1", gn_tab=t1)
+            t2 = self.gn_table(h1, p + ".norm2", what=p + ".norm2(table)")
+            if (p + ".conv_shortcut.w") in t:
+                out = self.conv3x3(h1, p + ".conv2.w", t[p + ".conv2.bias_sc"], cout,
+                                   shortcut=(x.t, p + ".conv_shortcut.w"), what=p + ".gn2+conv2+shortcut", gn_tab=t2)
+            else:
+                out = self.conv3x3(h1, p + ".conv2.w", t[p + ".conv2.bias"], cout, residual=x.t,
+                                   what=p + ".gn2+conv2+res", gn_tab=t2)
+            self.pool.put(t1)
+            self.pool.put(t2)
+            self.pool.put(h1.t)
+            self.pool.put(x.t)
+            return out
         a1 = self.gn(x, p + ".norm1", what=p + ".norm1")
         h1 = self.conv3x3(_Act(a1, None), p + ".conv1.w", t[p + ".conv1.bias"], cout, what=p + ".conv1")
         self.pool.put(a1)
