@@ -34,6 +34,8 @@ def main():
         ("plain", 192, 256, 256), ("residual", 192, 256, 256), ("plain", 192, 512, 256),
         ("plain", 96, 512, 512), ("residual", 96, 512, 512), ("residual", 48, 512, 512),
         ("up", 192, 256, 256), ("up", 96, 512, 512), ("down", 384, 128, 128),
+        ("gn", 384, 128, 128), ("gn+res", 384, 128, 128), ("gn", 384, 256, 128), ("gn+sc", 384, 128, 128),
+        ("gn", 192, 256, 256), ("gn+res", 96, 512, 512), ("gn+sc", 192, 256, 256),
     ]
     stream = torch.cuda.current_stream().cuda_stream
     if os.environ.get("CASE"):
@@ -54,6 +56,15 @@ def main():
             xs = torch.randn(n, hw, hw, 2 * cin, device=dev).half()
             t["tmp.sc"] = (torch.randn(1, cout, 2 * cin, device=dev) / math.sqrt(2 * cin)).half()
             hs.conv3x3(_Act(x, None), "tmp.w", bias, cout, shortcut=(xs, "tmp.sc"))
+        elif mode.startswith("gn"):
+            tab = torch.randn(n, cin, 2, device=dev) * 0.3 + 0.5
+            res = torch.randn(n, hw, hw, cout, device=dev).half() if mode == "gn+res" else None
+            sc = None
+            if mode == "gn+sc":
+                xs = torch.randn(n, hw, hw, 2 * cin, device=dev).half()
+                t["tmp.sc"] = (torch.randn(1, cout, 2 * cin, device=dev) / math.sqrt(2 * cin)).half()
+                sc = (xs, "tmp.sc")
+            hs.conv3x3(_Act(x, None), "tmp.w", bias, cout, residual=res, shortcut=sc, gn_tab=tab)
         elif mode == "up":
             t["tmp.w"] = PackedAKL._phase_weights(wt)
             hs.upsample(_Act(x, None), "tmp.w", bias)

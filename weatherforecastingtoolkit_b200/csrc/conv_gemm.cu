@@ -43,7 +43,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 // function of the shared-memory address -- probed in csrc/debug_mma.cu), so activations are staged once
 // instead of once per tap and the weight tiles stream through their own ring.
 constexpr int kHaloRows = 18;
-constexpr int kHaloBStages = 8;
+constexpr int kHaloBStagesMax = 8;
 
 struct ConvKernelParams {
   CUtensorMap a_map[2];
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
   constexpr int kHaloBytes = kHaloPitch * kHaloRows * 128;
   constexpr int kHaloStage = (kHaloBytes + 1023) & ~1023;
   constexpr int kStageBytes = HALO ? kHaloStage : MB * kABytes + kBBytes;
-  constexpr int kBStages = HALO ? kHaloBStages : 0;
+  constexpr int kBStages = HALO ? (MB == 1 ? 6 : 5) : 0;  // weight-tile ring depth (16 KB / 8 KB tiles)
   constexpr int kFirstEpiWarp = HALO ? 3 + kXformWarps : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -214,20 +214,28 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
           const TileCoord t = decode_tile(p, tile);
           const int x0 = (t.tx * kBlocksPerTile + static_cast<int>(cta_rank) * MB) * 8;
           const int y0 = t.ty * 16;
-          for (int seg = 0; seg < 2; ++seg) {
+          // all K blocks of source 0 (every tap), then those of source 1 (fused 1x1 shortcut, centre tap)
+          auto step = [&](const int seg, const int kb) {
             const CUtensorMap* am = &p.a_map[seg];
-            for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
+            
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               uint8_t* sa = smem + stage * kStageBytes;
-              // each CTA's box completes on its OWN barrier: its transform warps consume it first
-              mbar_arrive_expect_tx(&full_bar[stage], kHaloBytes);
-              tma_load_5d(sa, am, &full_bar[stage], kb * kBlockK, x0 - 1, 0, y0 - 1, t.frame * p.a_frame_mul);
+              // each CTA's box completes on its OWN barrier: its transform warps consume it first.
+              // Source 1 (1x1 shortcut, centre tap only) needs no halo: a plain (8*MB) x 16 pixel box.
+              if (seg == 0) {
+                mbar_arrive_expect_tx(&full_bar[stage], kHaloBytes);
+                tma_load_5d(sa, am, &full_bar[stage], kb * kBlockK, x0 - 1, 0, y0 - 1, t.frame * p.a_frame_mul);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], MB * kABytes);
+                tma_load_5d(sa, am, &full_bar[stage], kb * kBlockK, x0, 0, y0, t.frame * p.a_frame_mul);
+              }
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
               }
-            }
-          }
+            };
+          for (int i0 = 0; i0 < p.seg_kblocks[0]; ++i0) step(0, i0);
+          for (int j1 = 0; j1 < p.seg_kblocks[1]; ++j1) step(1, j1);
         }
       } else
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
@@ -292,7 +300,8 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
       const uint32_t idesc = p.idesc;
       if (HALO) {
         // A descriptors: start = halo base + (r*pitch + 8*mb + s) rows, 8-row groups `pitch` rows apart
-        const uint32_t a_hi = (desc_hi & ~0x3FFFu) | static_cast<uint32_t>((kHaloPitch * 128) >> 4);
+        const uint32_t a_hi0 = (desc_hi & ~0x3FFFu) | static_cast<uint32_t>((kHaloPitch * 128) >> 4);
+        const uint32_t a_hi1 = (desc_hi & ~0x3FFFu) | static_cast<uint32_t>((8 * MB * 128) >> 4);  // shortcut box pitch
         const uint32_t b_lo0 = lo0 + ((STAGES * kStageBytes) >> 4);
         int bstage = 0;
         uint32_t bphase = 0;
@@ -302,14 +311,16 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MB * BN);
           uint32_t accumulate = 0;
-          for (int seg = 0; seg < 2; ++seg) {
+          // all K blocks of source 0 (every tap), then those of source 1 (fused 1x1 shortcut, centre tap)
+          auto step = [&](const int seg, const int kb) {
             const int ntaps = seg == 0 ? p.taps_per_phase : 1;
-            for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
+            const uint32_t a_hi = seg == 0 ? a_hi0 : a_hi1;
+            
               mbar_wait(&ready_bar[stage], phase);
               tc_fence_after();
               const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
               for (int ti = 0; ti < ntaps; ++ti) {
-                int r = 1, sx = 1;
+                int r = 0, sx = 0;  // source 1: the box starts at the block origin
                 if (seg == 0) {
                   const wfk_tap tap = p.taps[t.phase * p.taps_per_phase + ti];
                   r = tap.dy + 1;
@@ -319,17 +330,18 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(bstage) * (kBBytes >> 4);
                 const uint32_t a_tap = a_lo + static_cast<uint32_t>((r * kHaloPitch + sx) * 8);  // rows * 128 B >> 4
+                // the 4 K slices of one pixel block are issued back to back (same accumulator)
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
+                for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-                  for (int mb = 0; mb < MB; ++mb) {
+                  for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
                     const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_tap + static_cast<uint32_t>(mb * 64 + 2 * k));
-                    if (PAIR) umma_f16_2sm(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
-                    else umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
+                    if (PAIR) umma_f16_2sm(d_tmem + mb * BN, adesc, bdesc, idesc, (k > 0) ? 1u : accumulate);
+                    else umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, (k > 0) ? 1u : accumulate);
                   }
-                  accumulate = 1;
                 }
+                accumulate = 1;
                 if (PAIR) umma_commit_2sm(&bempty_bar[bstage]);
                 else umma_commit(&bempty_bar[bstage]);
                 if (++bstage == kBStages) {
@@ -343,8 +355,9 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
                 stage = 0;
                 phase ^= 1u;
               }
-            }
-          }
+            };
+          for (int i0 = 0; i0 < p.seg_kblocks[0]; ++i0) step(0, i0);
+          for (int j1 = 0; j1 < p.seg_kblocks[1]; ++j1) step(1, j1);
           if (PAIR) umma_commit_2sm(&tfull_bar[acc]);
           else umma_commit(&tfull_bar[acc]);
           acc ^= 1;
@@ -398,10 +411,11 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
       uint32_t bphase = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
-        for (int seg = 0; seg < 2; ++seg) {
+        // all K blocks of source 0 (every tap), then those of source 1 (fused 1x1 shortcut, centre tap)
+        auto step = [&](const int seg, const int kb) {
           const CUtensorMap* bm = &p.b_map[seg];
           const int ntaps = seg == 0 ? p.taps_per_phase : 1;
-          for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
+          
             for (int ti = 0; ti < ntaps; ++ti) {
               const int slab = (seg == 0 ? p.taps[t.phase * p.taps_per_phase + ti].b_slab : p.seg1_slab) +
                                t.frame * p.b_frame_mul;
@@ -420,8 +434,9 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
                 bphase ^= 1u;
               }
             }
-          }
-        }
+          };
+        for (int i0 = 0; i0 < p.seg_kblocks[0]; ++i0) step(0, i0);
+        for (int j1 = 0; j1 < p.seg_kblocks[1]; ++j1) step(1, j1);
       }
     }
   } else if (HALO && warp < 3 + kXformWarps) {
@@ -437,8 +452,9 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
       const TileCoord t = decode_tile(p, tile);
       const int x0 = (t.tx * kBlocksPerTile + static_cast<int>(cta_rank) * MB) * 8 - 1;
       const int y0 = t.ty * 16 - 1;
-      for (int seg = 0; seg < 2; ++seg) {
-        for (int kb = 0; kb < p.seg_kblocks[seg]; ++kb) {
+      // all K blocks of source 0 (every tap), then those of source 1 (fused 1x1 shortcut, centre tap)
+      auto step = [&](const int seg, const int kb) {
+        
           mbar_wait(&full_bar[stage], phase);
           if (seg == 0 && p.gn_table != nullptr) {
             float ga[8], gb[8];
@@ -456,7 +472,7 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
             for (int row = xt >> 3; row < kHaloPitch * kHaloRows; row += (32 * kXformWarps) >> 3) {
               const int hy = row / kHaloPitch, hx = row - hy * kHaloPitch;
               const int py = y0 + hy, px = x0 + hx;
-              if (py < 0 || py >= p.tile_h || px < 0 || px >= p.tile_w) continue;
+              if (py < 0 || py >= p.tile_h || px < 0 || px >= p.tile_w) continue;  // zero padding stays zero
               uint4* cp = reinterpret_cast<uint4*>(sa + row * 128 + ((lc ^ (row & 7)) << 4));
               uint4 u = *cp;
               __half2* h2 = reinterpret_cast<__half2*>(&u);
@@ -482,8 +498,9 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
             stage = 0;
             phase ^= 1u;
           }
-        }
-      }
+        };
+      for (int i0 = 0; i0 < p.seg_kblocks[0]; ++i0) step(0, i0);
+      for (int j1 = 0; j1 < p.seg_kblocks[1]; ++j1) step(1, j1);
     }
   } else {
     // -------------------------------------------------------------- epilogue (8 warps)
@@ -681,11 +698,11 @@ struct ConvCfg<128, true, false> {
 };
 template <>
 struct ConvCfg<256, true, true> {
-  static constexpr int kMB = 1, kStages = 3;   // 3 x 23 KB halo boxes + 8 x 16 KB weight tiles
+  static constexpr int kMB = 1, kStages = 5;   // 5 x 23 KB halo boxes + 6 x 16 KB weight tiles
 };
 template <>
 struct ConvCfg<128, true, true> {
-  static constexpr int kMB = 2, kStages = 3;   // 3 x 41 KB halo boxes + 8 x 8 KB weight tiles
+  static constexpr int kMB = 2, kStages = 4;   // 4 x 41 KB halo boxes + 5 x 8 KB weight tiles
 };
 
 template <int BN, bool PAIR, bool HALO>
@@ -693,9 +710,9 @@ constexpr size_t conv_smem_bytes() {
   using Cfg = ConvCfg<BN, PAIR, HALO>;
   constexpr size_t b_bytes = static_cast<size_t>(PAIR ? BN / 2 : BN) * kBlockK * 2;
   constexpr size_t halo_stage = (static_cast<size_t>(8 * Cfg::kMB + 2) * kHaloRows * 128 + 1023) & ~static_cast<size_t>(1023);
-  constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + kHaloBStages * b_bytes
+  constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + (Cfg::kMB == 1 ? 6 : 5) * b_bytes
                                : Cfg::kStages * (Cfg::kMB * kABytes + b_bytes);
-  return 1024 /*align slack*/ + ring + (3 * Cfg::kStages + 2 * kHaloBStages + 4) * 8 + 16 +
+  return 1024 /*align slack*/ + ring + (3 * Cfg::kStages + 2 * kHaloBStagesMax + 4) * 8 + 16 +
          kEpiWarps * (BN / 2) * 4 + BN * 4 + 64;
 }
 
@@ -958,7 +975,8 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   int rc = encode_a(d->a[0], a_bw, a_bh, d->operand_bf16 != 0, &p.a_map[0]);
   if (rc == WFK_OK) rc = encode_b(d->b[0], b_rows, d->operand_bf16 != 0, &p.b_map[0]);
   if (rc == WFK_OK && uses_src1) {
-    rc = encode_a(d->a[1], a_bw, a_bh, d->operand_bf16 != 0, &p.a_map[1]);
+    rc = plan->halo ? encode_a(d->a[1], 8 * mb_cta, 16, d->operand_bf16 != 0, &p.a_map[1])
+                    : encode_a(d->a[1], a_bw, a_bh, d->operand_bf16 != 0, &p.a_map[1]);
     if (rc == WFK_OK) rc = encode_b(d->b[1], b_rows, d->operand_bf16 != 0, &p.b_map[1]);
   } else if (rc == WFK_OK) {
     p.a_map[1] = p.a_map[0];
