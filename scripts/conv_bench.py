@@ -34,6 +34,7 @@ def main():
         ("plain", 192, 256, 256), ("residual", 192, 256, 256), ("plain", 192, 512, 256),
         ("plain", 96, 512, 512), ("residual", 96, 512, 512), ("residual", 48, 512, 512),
         ("up", 192, 256, 256), ("up", 96, 512, 512), ("down", 384, 128, 128),
+        ("plain", 384, 128, 256), ("plain", 384, 128, 512),
         ("gn", 384, 128, 128), ("gn+res", 384, 128, 128), ("gn", 384, 256, 128), ("gn+sc", 384, 128, 128),
         ("gn", 192, 256, 256), ("gn+res", 96, 512, 512), ("gn+sc", 192, 256, 256),
     ]

@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const __half* _
 
 }  // namespace wfk
 
+int wfk_launch_c1in(const float* in, int n, int h, int w, const float* weight, const float* bias, int cout, void* out,
+                    double* stats, int cpg, cudaStream_t s);
+
 extern "C" int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int w, const float* pre_w,
                                      const float* pre_b, const float* weight, const float* bias, int cout, void* out,
                                      double* stats, int cpg, void* stream) {
@@ -213,6 +216,8 @@ extern "C" int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int
   WFK_REQUIRE((pre_w == nullptr) == (pre_b == nullptr), "pre_w / pre_b must both be given or both NULL");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0, "bad shape");
   if (stats) WFK_REQUIRE(cpg >= 4 && cout % cpg == 0 && (cpg == 4 || cpg % 8 == 0), "cpg=%d unsupported", cpg);
+  if (cin == 1 && pre_w == nullptr && 256 % (cout / 8) == 0 && (!stats || cpg == 4 || cpg % 8 == 0))
+    return wfk_launch_c1in(in, n, h, w, weight, bias, cout, out, stats, stats ? cpg : 8, static_cast<cudaStream_t>(stream));
   const int ppb = 64;
   dim3 grid((h * w + ppb - 1) / ppb, n);
   const size_t smem = 0;
