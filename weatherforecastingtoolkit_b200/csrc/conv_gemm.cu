@@ -55,6 +55,7 @@ struct ConvKernelParams {
   int seg1_slab;       // HALO: weight slab of the shortcut
   const float2* gn_table;  // HALO: [frame][cin] (scale, shift) of a fused GroupNorm+SiLU on source 0, or null
   int gn_cin;
+  int xform_debug;  // experiment switch: 1 = load/store without math, 2 = skip the transform entirely
   int num_phases, taps_per_phase;
   int a_frame_mul, b_frame_mul;
   const float* bias;
@@ -465,17 +466,18 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
       auto step = [&](const int seg, const int kb) {
         
           mbar_wait(&full_bar[stage], phase);
-          if (seg == 0 && p.gn_table != nullptr) {
+          if (seg == 0 && p.gn_table != nullptr && p.xform_debug != 2) {
             float ga[8], gb[8];
             const float4* tp = reinterpret_cast<const float4*>(p.gn_table + static_cast<int64_t>(t.frame) * p.gn_cin +
                                                                kb * kBlockK + lc * 8);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 v = __ldg(tp + j);
-              ga[2 * j] = v.x;
-              gb[2 * j] = v.y;
-              ga[2 * j + 1] = v.z;
-              gb[2 * j + 1] = v.w;
+              // silu(z) = h + h*tanh(h) with h = z/2: one MUFU op per element instead of two (ex2 + rcp)
+              ga[2 * j] = 0.5f * v.x;
+              gb[2 * j] = 0.5f * v.y;
+              ga[2 * j + 1] = 0.5f * v.z;
+              gb[2 * j + 1] = 0.5f * v.w;
             }
             uint8_t* sa = smem + stage * kStageBytes;
             for (int row = xt >> 3; row < kHaloPitch * kHaloRows; row += (32 * kXformWarps) >> 3) {
@@ -487,12 +489,14 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
               __half2* h2 = reinterpret_cast<__half2*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
+                if (p.xform_debug == 1) break;
                 float2 f = __half22float2(h2[e]);
-                f.x = fmaf(f.x, ga[2 * e], gb[2 * e]);
-                f.y = fmaf(f.y, ga[2 * e + 1], gb[2 * e + 1]);
-                f.x = __fdividef(f.x, 1.f + __expf(-f.x));
-                f.y = __fdividef(f.y, 1.f + __expf(-f.y));
-                h2[e] = __floats2half2_rn(f.x, f.y);
+                const float hx = fmaf(f.x, ga[2 * e], gb[2 * e]);
+                const float hy = fmaf(f.y, ga[2 * e + 1], gb[2 * e + 1]);
+                float tx, ty;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(hx));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(hy));
+                h2[e] = __floats2half2_rn(fmaf(hx, tx, hx), fmaf(hy, ty, hy));
               }
               *cp = u;
             }
@@ -955,6 +959,7 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.seg1_slab = slab1;
   p.gn_table = static_cast<const float2*>(d->gn_table);
   p.gn_cin = static_cast<int>(d->a[0].dim[0]);
+  p.xform_debug = std::getenv("WFK_XFORM_DEBUG") ? std::atoi(std::getenv("WFK_XFORM_DEBUG")) : 0;
   if (d->gn_table != nullptr && !plan->halo) {
     delete plan;
     return wfk::fail(WFK_ERR_INVALID, "a fused GroupNorm+SiLU input (gn_table) needs a HALO-eligible 3x3 stride-1 convolution");
