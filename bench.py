@@ -75,7 +75,7 @@ class ClockSampler:
             self.proc.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
@@ -84,6 +84,7 @@ class ClockSampler:
             try:
                 sm.append(float(parts[1]))
                 mx.append(float(parts[2]))
+                pw.append(float(parts[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, parts[5:9]):
@@ -96,7 +97,9 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        pw.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": pw[len(pw) // 2] if pw else None}
 
 
 # ------------------------------------------------------------------------------------ CPU arms
