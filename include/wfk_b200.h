@@ -63,6 +63,27 @@ int wfk_predict_linear(const float* lat, const float* weight, const float* bias,
                        int c, int hw, float* pred, float* tgt, double* loss_sums, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 8(f).1  DLinear latent predictor.  Replaces moving_avg / series_decomp / DLinear.forward and the
+ *     residual framing around it (experiments/v1_experiments/pretrained_ae_dlinear_sevir/train.py:
+ *     21-99, 179-192; individual=True: ../pretrained_ae_dlinear_ind/train.py, experiments/ae_s2/
+ *     train.py:55-133; the (t,c)-interleaved 52->48 form: ../pretrained_ae_dlinear_indc_indp/train.py:
+ *     56-99, 185-186).
+ *     framed != 0: x = latents [nb, (seq_len+pred_len)/group frames, ...] viewed as [nb][seq_len+pred_len]
+ *       [channels] (x_batch_stride elements between sequences); the last input frame is subtracted
+ *       before and added back after the predictor; writes pred [nb, pred_len, channels], optional tgt
+ *       (same shape) and loss_sums[2] (double: sum((pred-tgt)^2) in residual space, element count;
+ *       caller-zeroed).  group = 1: one series per (latent channel, pixel); group = C: series over
+ *       the interleaved (t, c) axis, one per pixel.
+ *     framed == 0: plain DLinear.forward, x [nb, seq_len, channels] -> pred [nb, pred_len, channels].
+ *     individual == 0: w_* [pred_len, seq_len], b_* [pred_len]; else w_* [channels, pred_len, seq_len],
+ *     b_* [channels, pred_len] (the stacked nn.ModuleList).  kernel_size odd (AvgPool1d window).
+ */
+int wfk_dlinear(const float* x, int64_t x_batch_stride, const float* w_seasonal, const float* b_seasonal,
+                const float* w_trend, const float* b_trend, int nb, int seq_len, int pred_len, int channels,
+                int group, int kernel_size, int individual, int framed, float* pred, float* tgt,
+                double* loss_sums, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a10-a14  Fused skill-score pass.  Replaces the 41 passes of calc_metrics
  *     (pipeline/metrics.py:86-133): clamp(0,1) (:92-93); _hit_miss_fa_cn counts (:9-16) at the
  *     fp32 thresholds for pools none / avg4 / avg16 (csi :43-54, hss :56-69, avg_pool2d :46-50);

@@ -1,0 +1,115 @@
+"""Golden fixtures for the components outside the headline Path-B linear rollout, generated from the
+UNMODIFIED reference (/root/reference; build container only). Run:
+
+    python tests/golden/make_golden_extra.py            # writes extra_golden.npz
+
+* DLinear predictors -- the class definitions live inside train scripts that import pytorch_lightning /
+  wandb / omegaconf (absent here), so ``ref_script_classes`` extracts the ``ClassDef`` nodes with ``ast`` and
+  executes exactly that source (no edits) in a namespace holding ``torch`` / ``nn`` / ``F``.
+* NLayerDiscriminator (pipeline/models/autoencoderkl/losses/model.py), PosAwareAE_TF
+  (pipeline/models/ae_64x8x8_lin.py), AE_ViT_2048 (pipeline/models/ae_vit.py) are imported directly.
+
+Inputs and weights are regenerated from seeds at test time (``weatherforecastingtoolkit_b200.synthetic``);
+only reference OUTPUTS are stored.
+"""
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = "/root/reference"
+sys.dont_write_bytecode = True
+sys.path.insert(0, REFERENCE)
+sys.path.insert(0, ROOT)
+
+from weatherforecastingtoolkit_b200 import synthetic as S  # noqa: E402
+
+
+def ref_script_classes(rel_path, names):
+    """Execute the named top-level class definitions of a reference script, unmodified."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    src = open(os.path.join(REFERENCE, rel_path)).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "nn": nn, "F": F}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), rel_path, "exec"), ns)
+    missing = [n for n in names if n not in ns]
+    assert not missing, missing
+    return ns
+
+
+DLINEAR_SCRIPTS = {
+    "shared": "experiments/v1_experiments/pretrained_ae_dlinear_sevir/train.py",
+    "individual": "experiments/v1_experiments/pretrained_ae_dlinear_ind/train.py",
+    "indc_indp": "experiments/v1_experiments/pretrained_ae_dlinear_indc_indp/train.py",
+}
+
+
+def ref_dlinear(variant, cfg, params):
+    """Reference DLinear module of `variant` with the synthetic parameters loaded."""
+    ns = ref_script_classes(DLINEAR_SCRIPTS[variant], ["moving_avg", "series_decomp", "DLinear"])
+    m = ns["DLinear"](cfg)
+    ws, bs, wt, bt = params
+    with torch.no_grad():
+        if cfg.individual:
+            for i in range(cfg.enc_in):
+                m.Linear_Seasonal[i].weight.copy_(ws[i])
+                m.Linear_Seasonal[i].bias.copy_(bs[i])
+                m.Linear_Trend[i].weight.copy_(wt[i])
+                m.Linear_Trend[i].bias.copy_(bt[i])
+        else:
+            m.Linear_Seasonal.weight.copy_(ws)
+            m.Linear_Seasonal.bias.copy_(bs)
+            m.Linear_Trend.weight.copy_(wt)
+            m.Linear_Trend.bias.copy_(bt)
+    return m.eval()
+
+
+def ref_dlinear_step(m, lat, variant, in_frames=13):
+    """validation_step algebra around the predictor (pretrained_ae_dlinear_sevir/train.py:179-192;
+    indc_indp: train.py:179-192 with the (t c) reshape)."""
+    b, t, c, h, w = lat.shape
+    inp, tgt = lat[:, :in_frames], lat[:, in_frames:]
+    inp_t = inp[:, -1].unsqueeze(1)
+    inp = inp - inp_t
+    tgt = tgt - inp_t
+    if variant == "indc_indp":
+        pred = m(inp.reshape(b, in_frames * c, h * w))
+    else:
+        pred = m(inp.reshape(b, in_frames, c * h * w))
+    pred = pred.reshape(b, t - in_frames, c, h, w)
+    loss = torch.nn.functional.mse_loss(pred, tgt)
+    return pred + inp_t, tgt + inp_t, loss
+
+
+def gen_dlinear(out):
+    for variant in ("shared", "individual", "indc_indp"):
+        cfg, params, lat = S.make_dlinear_case(variant)
+        m = ref_dlinear(variant, cfg, params)
+        with torch.no_grad():
+            pred, tgt, loss = ref_dlinear_step(m, lat, variant)
+        out[f"dlinear_{variant}_pred"] = pred.numpy()
+        out[f"dlinear_{variant}_tgt"] = tgt.numpy()
+        out[f"dlinear_{variant}_loss"] = np.array(loss.item())
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    out = {}
+    gen_dlinear(out)
+    for fn in EXTRA_GENERATORS:
+        fn(out)
+    np.savez_compressed(os.path.join(HERE, "extra_golden.npz"), **{k: np.asarray(v, dtype=np.float32) for k, v in out.items()})
+    print("wrote extra_golden.npz:", {k: v.shape for k, v in out.items()})
+
+
+EXTRA_GENERATORS = []
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,9 @@ _PROTOTYPES = {
     "wfk_stage_vil_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "wfk_predict_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wfk_dlinear": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p]),
     "wfk_metrics_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "wfk_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
                               C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -1,0 +1,149 @@
+"""DLinear latent predictors behind the reference experiments' ``self.predictor`` interface.
+
+Mirrors the script-local ``DLinear`` modules of the reference (paths relative to the reference repo):
+
+* ``experiments/v1_experiments/pretrained_ae_dlinear_sevir/train.py:21-99`` -- shared weights,
+  ``Linear(13, 12)`` per series, ``enc_in`` = 4*48*48 series, kernel 3;
+* ``experiments/v1_experiments/pretrained_ae_dlinear_ind/train.py`` and ``experiments/ae_s2/train.py:
+  55-133`` -- ``individual=True``: one ``nn.Linear`` per series in an ``nn.ModuleList``, run by a Python loop;
+* ``experiments/v1_experiments/pretrained_ae_dlinear_indc_indp/train.py:56-99`` -- the series axis is the
+  interleaved (t, c) axis: ``Linear(13*4, 12*4)`` per latent pixel, kernel 5 (``DLinearIndcIndp``).
+
+Parameter names / shapes (hence ``state_dict`` keys) are the reference's, including its unused
+``Linear_Decoder``. ``forward`` and ``rollout`` run ``wfk_dlinear`` (one fused kernel, no permute / cat /
+per-series Python loop); there is no CPU path.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+
+def _cfg(configs, name, default=None):
+    if isinstance(configs, dict):
+        return configs.get(name, default)
+    return getattr(configs, name, default)
+
+
+class _DLinearBase(nn.Module):
+    """Shared host logic; ``mult`` = 1 (series over t) or the latent channel count (series over (t, c))."""
+
+    def __init__(self, configs, mult: int, with_decoder: bool):
+        super().__init__()
+        self.seq_len = int(_cfg(configs, "seq_len"))
+        self.pred_len = int(_cfg(configs, "pred_len"))
+        self.kernel_size = int(_cfg(configs, "kernel_size"))
+        self.individual = bool(_cfg(configs, "individual"))
+        self.channels = int(_cfg(configs, "enc_in"))
+        self.mult = int(mult)
+        if self.kernel_size % 2 == 0:
+            raise ValueError("kernel_size must be odd (the reference's moving_avg pads (k-1)//2 on both ends)")
+        L, P = self.seq_len * self.mult, self.pred_len * self.mult
+        init = (1.0 / L) * torch.ones(P, L)   # train.py:75-77 / indc_indp train.py:73-76
+
+        def lin():
+            m = nn.Linear(L, P)
+            m.weight = nn.Parameter(init.clone())
+            return m
+
+        if self.individual:
+            self.Linear_Seasonal = nn.ModuleList([lin() for _ in range(self.channels)])
+            self.Linear_Trend = nn.ModuleList([lin() for _ in range(self.channels)])
+            if with_decoder:
+                self.Linear_Decoder = nn.ModuleList([nn.Linear(L, P) for _ in range(self.channels)])
+        else:
+            self.Linear_Seasonal = lin()
+            self.Linear_Trend = lin()
+            if with_decoder:
+                self.Linear_Decoder = nn.Linear(L, P)
+        self._packed = None
+
+    # ------------------------------------------------------------------ weights in kernel layout
+    def _pack(self, device) -> Tuple[torch.Tensor, ...]:
+        """fp32 device copies: shared [P, L] / [P]; individual: the ModuleList stacked to [channels, P, L] /
+        [channels, P]. Cached until a parameter changes (version counters)."""
+        mods = (list(self.Linear_Seasonal) + list(self.Linear_Trend)) if self.individual else \
+            [self.Linear_Seasonal, self.Linear_Trend]
+        key = (str(device), sum(p._version for m in mods for p in (m.weight, m.bias)),
+               tuple(p.data_ptr() for m in (mods[0], mods[-1]) for p in (m.weight, m.bias)))
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[1]
+        with torch.no_grad():
+            if self.individual:
+                n = self.channels
+                ws = torch.stack([m.weight for m in mods[:n]]).to(device=device, dtype=torch.float32).contiguous()
+                bs = torch.stack([m.bias for m in mods[:n]]).to(device=device, dtype=torch.float32).contiguous()
+                wt = torch.stack([m.weight for m in mods[n:]]).to(device=device, dtype=torch.float32).contiguous()
+                bt = torch.stack([m.bias for m in mods[n:]]).to(device=device, dtype=torch.float32).contiguous()
+            else:
+                ws, bs, wt, bt = (t.detach().to(device=device, dtype=torch.float32).contiguous()
+                                  for t in (mods[0].weight, mods[0].bias, mods[1].weight, mods[1].bias))
+        self._packed = (key, (ws, bs, wt, bt))
+        return self._packed[1]
+
+    def _launch(self, x: torch.Tensor, batch_stride: int, nb: int, framed: bool, pred, tgt, loss):
+        if not x.is_cuda:
+            raise RuntimeError("this path runs on a B200 only (no CPU fallback): pass CUDA tensors")
+        lib = _cabi.init(x.device.index if x.device.index is not None else 0)
+        ws, bs, wt, bt = self._pack(x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _cabi.check(lib.wfk_dlinear(x.data_ptr(), batch_stride, ws.data_ptr(), bs.data_ptr(), wt.data_ptr(), bt.data_ptr(),
+                                    nb, self.seq_len * self.mult, self.pred_len * self.mult, self.channels, self.mult,
+                                    self.kernel_size, 1 if self.individual else 0, 1 if framed else 0, pred.data_ptr(),
+                                    None if tgt is None else tgt.data_ptr(), None if loss is None else loss.data_ptr(),
+                                    stream), "wfk_dlinear")
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [Batch, Input length, Channel] -> [Batch, Output length, Channel] (DLinear.forward, train.py:81-97)."""
+        L, P = self.seq_len * self.mult, self.pred_len * self.mult
+        if x.ndim != 3 or x.shape[1] != L or x.shape[2] != self.channels:
+            raise ValueError(f"expected [B, {L}, {self.channels}], got {tuple(x.shape)}")
+        x = x.detach().to(torch.float32).contiguous()
+        out = torch.empty((x.shape[0], P, self.channels), dtype=torch.float32, device=x.device)
+        self._launch(x, L * self.channels, x.shape[0], False, out, None, None)
+        return out
+
+    @torch.no_grad()
+    def rollout(self, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """v [B, seq_len + pred_len, C, h, w] fp32 latents -> (pred, tgt, val_loss): the validation_step algebra
+        (train.py:179-192) in one pass -- subtract the last input frame, DLinear, add it back; F.mse_loss of the
+        residual-space prediction."""
+        b, t, c, h, w = v.shape
+        if t != self.seq_len + self.pred_len:
+            raise ValueError(f"latents have {t} frames, predictor expects {self.seq_len}+{self.pred_len}")
+        if self.mult not in (1, c) or self.channels * self.mult != c * h * w:
+            raise ValueError(f"latents {tuple(v.shape)} do not match enc_in={self.channels} (x{self.mult})")
+        v = v.detach().to(torch.float32).contiguous()
+        pred = torch.empty((b, self.pred_len, c, h, w), dtype=torch.float32, device=v.device)
+        tgt = torch.empty_like(pred)
+        loss = torch.zeros(2, dtype=torch.float64, device=v.device)
+        self._launch(v, t * c * h * w, b, True, pred, tgt, loss)
+        return pred, tgt, (loss[0] / loss[1]).to(torch.float32)
+
+
+class DLinear(_DLinearBase):
+    """``DLinear(configs)`` of pretrained_ae_dlinear_sevir / pretrained_ae_dlinear_ind / ae_s2: configs has
+    ``seq_len, pred_len, individual, enc_in, kernel_size``."""
+
+    def __init__(self, configs):
+        super().__init__(configs, mult=1, with_decoder=True)
+
+
+class DLinearIndcIndp(_DLinearBase):
+    """``DLinear(configs)`` of pretrained_ae_dlinear_indc_indp: linears are ``Linear(seq_len*4, pred_len*4)``
+    over the interleaved (t, c) axis (train.py:70-79); ``enc_in`` = latent pixels."""
+
+    def __init__(self, configs, latent_channels: int = 4):
+        super().__init__(configs, mult=latent_channels, with_decoder=False)
+
+
+def dlinear_config(seq_len=13, pred_len=12, individual=False, enc_in=9216, kernel_size=3) -> SimpleNamespace:
+    """The ``dlinear:`` block of the reference configs (e.g. pretrained_ae_dlinear_sevir/config.yaml:4-9)."""
+    return SimpleNamespace(seq_len=seq_len, pred_len=pred_len, individual=individual, enc_in=enc_in,
+                           kernel_size=kernel_size)

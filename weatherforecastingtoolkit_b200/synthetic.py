@@ -203,3 +203,36 @@ def make_vil_sequences(n: int, h: int = 384, w: int = 384, t: int = 25, seed: in
         v = torch.clamp(f * 110.0, 0.0, 255.0)
         out[..., ti] = v.round().to(torch.uint8)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# DLinear predictors (reference: experiments/v1_experiments/pretrained_ae_dlinear_*/train.py)
+def _uniform(shape, name: str, seed: int, bound: float) -> torch.Tensor:
+    g = torch.Generator().manual_seed(_name_seed(name, seed))
+    return ((torch.rand(shape, generator=g) * 2.0 - 1.0) * bound).float()
+
+
+def make_dlinear_case(variant: str, seed: int = 0, batch: int = 2, c: int = 4, h: int = 6, w: int = 5):
+    """Small DLinear parity case: (configs, (w_seasonal, b_seasonal, w_trend, b_trend), latents [B,25,C,h,w]).
+
+    ``shared`` / ``individual``: series over t (13 -> 12), enc_in = C*h*w, kernel 3
+    (pretrained_ae_dlinear_sevir / _ind config.yaml:4-9); ``indc_indp``: series over the interleaved
+    (t, c) axis (52 -> 48), enc_in = h*w, kernel 5, individual (pretrained_ae_dlinear_indc_indp/config.yaml).
+    Weights are random (the reference's 1/L constant init would hide index bugs)."""
+    from types import SimpleNamespace
+    if variant == "indc_indp":
+        cfg = SimpleNamespace(seq_len=INPUT_FRAMES, pred_len=PRED_FRAMES, individual=True, enc_in=h * w, kernel_size=5)
+        L, P = INPUT_FRAMES * c, PRED_FRAMES * c
+    elif variant in ("shared", "individual"):
+        cfg = SimpleNamespace(seq_len=INPUT_FRAMES, pred_len=PRED_FRAMES, individual=variant == "individual",
+                              enc_in=c * h * w, kernel_size=3)
+        L, P = INPUT_FRAMES, PRED_FRAMES
+    else:
+        raise ValueError(variant)
+    bound = 1.0 / math.sqrt(L)
+    lead = (cfg.enc_in,) if cfg.individual else ()
+    params = tuple(_uniform(lead + shp, f"dlinear.{variant}.{nm}", seed, bound)
+                   for nm, shp in (("ws", (P, L)), ("bs", (P,)), ("wt", (P, L)), ("bt", (P,))))
+    g = torch.Generator().manual_seed(_name_seed(f"dlinear.{variant}.lat", seed))
+    lat = torch.randn((batch, INPUT_FRAMES + PRED_FRAMES, c, h, w), generator=g).float()
+    return cfg, params, lat
