@@ -153,6 +153,15 @@ typedef struct wfk_view3 {
 
 #define WFK_MAX_TAPS 40
 
+/* Epilogue activations (conv-GEMM `act` / `act2`, the direct edge kernels' `act`). */
+enum wfk_act {
+  WFK_ACT_NONE = 0,
+  WFK_ACT_LEAKY_RELU = 1, /* slope = act_slope (nn.LeakyReLU(0.2), losses/model.py:121)          */
+  WFK_ACT_GELU = 2,       /* exact erf form (nn.GELU(), ae_64x8x8_lin.py:15, ae_vit.py:112)       */
+  WFK_ACT_SIGMOID = 3,    /* nn.Sigmoid (ae_64x8x8_lin.py:85)                                      */
+  WFK_ACT_SILU = 4
+};
+
 typedef struct wfk_conv_desc {
   wfk_view5 a[2];
   wfk_view3 b[2];
@@ -176,6 +185,17 @@ typedef struct wfk_conv_desc {
   int32_t operand_bf16;  /* 0: fp16 operands (default), 1: bf16 operands                        */
   const void* gn_table;  /* optional fused GroupNorm+SiLU on A source 0 (3x3 stride-1 convs only):
                             [n_frames][cin] float2 (scale, shift) from wfk_gn_table, or NULL          */
+  /* Extended epilogue (eval-mode BatchNorm folded into weights/bias by the caller):
+   *   v = act(D + bias (+ residual))            -> out_h / out_f / stats
+   *   out2_h = act2(scale2[c] * v + shift2[c])  -> a second fp16 tensor, same addressing as out_h
+   * e.g. a pre-activation bottleneck's x (raw, the residual) and gelu(bn1(x)) (the next conv's input)
+   * from one pass (ae_64x8x8_lin.py:14-23); LeakyReLU after conv+BN (losses/model.py:126-139). */
+  int32_t act;           /* wfk_act on the primary result                                       */
+  int32_t act2;          /* wfk_act on the secondary result                                     */
+  float act_slope;       /* LeakyReLU slope                                                     */
+  void* out2_h;          /* fp16 or NULL                                                        */
+  const float* scale2;   /* [n_total] or NULL (= 1)                                             */
+  const float* shift2;   /* [n_total] or NULL (= 0)                                             */
 } wfk_conv_desc;
 
 typedef struct wfk_conv_plan wfk_conv_plan;
@@ -209,6 +229,35 @@ int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int w, const f
 int wfk_conv3x3_small_cout(const void* in, int n, int h, int w, int cin, const void* weight_h,
                            const float* bias, int cout, const float* post_w, const float* post_b, float* out,
                            void* stream);
+
+/* Same with an output activation (WFK_ACT_NONE or WFK_ACT_SIGMOID): PosAwareAE_TF's
+ * dec[-1] Conv2d(128, 1, 3, padding=1) + Sigmoid (pipeline/models/ae_64x8x8_lin.py:83-85, 105). */
+int wfk_conv3x3_small_cout_act(const void* in, int n, int h, int w, int cin, const void* weight_h,
+                               const float* bias, int cout, const float* post_w, const float* post_b, int act,
+                               float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a16 / a17  Stem and head kernels of PosAwareAE_TF and NLayerDiscriminator (eval-mode BatchNorm
+ * folded into weight / bias by the caller).
+ *
+ * Conv2d(1, cout, 4, stride 2, padding 1) (+BN) + activation on an fp32 frame: enc[0].down of
+ * PosAwareAE_TF (ae_64x8x8_lin.py:31-34) and main[0..1] of NLayerDiscriminator (losses/model.py:121).
+ * in [n, 1, h, w] fp32 (h, w even); weight [16][cout] fp32 (tap r*4+s major); bias [cout];
+ * out [n, h/2, w/2, cout] fp16 NHWC = act(conv + bias); optional out2 = act2(scale2*out + shift2). */
+int wfk_conv4x4s2_c1in(const float* in, int n, int h, int w, const float* weight, const float* bias, int cout,
+                       int act, float act_slope, void* out, int act2, const float* scale2, const float* shift2,
+                       void* out2, void* stream);
+
+/* Conv2d(cin, 1, kernel 1, padding pad): NLayerDiscriminator's logit head (losses/model.py:149-150; the
+ * reference pads a 1x1 convolution, so the border ring of the output is the bare bias).
+ * in [n, h, w, cin] fp16 NHWC; weight [cin] fp32; out [n, 1, h+2*pad, w+2*pad] fp32. */
+int wfk_conv1x1_cout1(const void* in, int n, int h, int w, int cin, const float* weight, float bias, int pad,
+                      float* out, void* stream);
+
+/* Reductions behind the discriminator losses (losses/contperceptual.py:19-23 hinge_d_loss; g_loss =
+ * -mean(logits_fake), experiments/v1_experiments/ae_gan_kl/train.py:84-85): sums[0] += sum x,
+ * sums[1] += sum relu(1 - x), sums[2] += sum relu(1 + x) over count values (double, caller-zeroed). */
+int wfk_logit_sums(const float* x, int64_t count, double* sums, void* stream);
 
 /* Decoder tail, fused: GroupNorm(groups, eps) + SiLU + conv3x3(c -> 1, pad 1).  Replaces
  * conv_norm_out + conv_act + conv_out of Decoder.forward (vae.py:162-164).  x: [n, h, w, c] fp16 raw

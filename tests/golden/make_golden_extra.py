@@ -99,6 +99,30 @@ def gen_dlinear(out):
         out[f"dlinear_{variant}_loss"] = np.array(loss.item())
 
 
+def disc_inputs(n, hw, seed):
+    u8 = S.make_vil_sequences(n, hw, hw, 2, seed=seed)
+    x = ((1 / 255) * u8.float()).permute(0, 3, 1, 2).contiguous()
+    return x[:, :1].contiguous(), x[:, 1:2].contiguous()
+
+
+def gen_discriminator(out):
+    from pipeline.models.autoencoderkl.losses.model import NLayerDiscriminator
+    from pipeline.models.autoencoderkl.losses import model as RM  # noqa: F401  (contperceptual pulls lpips: not imported)
+    sd = S.make_discriminator_state_dict()
+    m = NLayerDiscriminator(input_nc=1, ndf=64, n_layers=3).eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        for tag, n, hw, seed in (("disc64", 2, 64, 41), ("disc384", 1, 384, 42)):
+            real, fake = disc_inputs(n, hw, seed)
+            lr, lf = m(real), m(fake)
+            out[f"{tag}_logits_real"] = lr.numpy()
+            out[f"{tag}_logits_fake"] = lf.numpy()
+            # hinge_d_loss (losses/contperceptual.py:19-23; that module cannot be imported here: it pulls lpips.py,
+            # which writes into the read-only tree) -- three reference lines restated:
+            d_loss = 0.5 * (torch.mean(torch.nn.functional.relu(1. - lr)) + torch.mean(torch.nn.functional.relu(1. + lf)))
+            out[f"{tag}_hinge"] = np.array(d_loss.item())
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     out = {}
@@ -109,7 +133,7 @@ def main():
     print("wrote extra_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
-EXTRA_GENERATORS = []
+EXTRA_GENERATORS = [gen_discriminator]
 
 if __name__ == "__main__":
     main()

@@ -54,7 +54,12 @@ class ConvDesc(C.Structure):
         ("out_rows", C.c_int32), ("out_cols", C.c_int32), ("out_sy", C.c_int32), ("out_sx", C.c_int32),
         ("ldc", C.c_int32), ("cpg", C.c_int32), ("operand_bf16", C.c_int32),
         ("gn_table", C.c_void_p),
+        ("act", C.c_int32), ("act2", C.c_int32), ("act_slope", C.c_float),
+        ("out2_h", C.c_void_p), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
     ]
+
+
+ACT_NONE, ACT_LEAKY_RELU, ACT_GELU, ACT_SIGMOID, ACT_SILU = range(5)
 
 
 _PROTOTYPES = {
@@ -83,6 +88,13 @@ _PROTOTYPES = {
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "wfk_conv3x3_small_cout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wfk_conv3x3_small_cout_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "wfk_conv4x4s2_c1in": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wfk_conv1x1_cout1": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int,
+                                    C.c_void_p, C.c_void_p]),
+    "wfk_logit_sums": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "wfk_gn_silu_conv3x3_c1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "wfk_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),

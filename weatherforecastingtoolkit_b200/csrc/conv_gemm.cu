@@ -66,6 +66,12 @@ struct ConvKernelParams {
   double* stats;
   int out_rows, out_cols, out_sy, out_sx, ldc;
   int cpg_log2, groups_total;
+  // EPI kernels only: v = act(acc + bias (+ residual)) -> out_h / out_f;  out2_h = act2(scale2[c] * v + shift2[c])
+  int act, act2;
+  float act_slope;
+  __half* out2_h;
+  const float* scale2;
+  const float* shift2;
   uint32_t idesc;
   wfk_tap taps[WFK_MAX_TAPS];
 };
@@ -92,6 +98,17 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
   t.ty = r / p.tiles_x;
   t.tx = r - t.ty * p.tiles_x;
   return t;
+}
+
+// Epilogue activations of the EPI kernels (wfk_act in the C ABI).
+__device__ __forceinline__ float act_apply(int kind, float x, float slope) {
+  switch (kind) {
+    case WFK_ACT_LEAKY_RELU: return x > 0.f ? x : slope * x;
+    case WFK_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));  // nn.GELU() default (erf form)
+    case WFK_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    case WFK_ACT_SILU: return x / (1.f + __expf(-x));
+    default: return x;
+  }
 }
 
 // Sum / sum-of-squares of 32 consecutive channels (one accumulator row chunk per lane) reduced over
@@ -140,7 +157,7 @@ __device__ __forceinline__ void chunk_group_stats(const float (&v)[32], bool val
   }
 }
 
-template <int BN, int MB, int STAGES, bool PAIR, bool HALO>
+template <int BN, int MB, int STAGES, bool PAIR, bool HALO, bool EPI>
 __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1)
     conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
@@ -181,6 +198,8 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [kEpiWarps][BN/4 groups max][2], 16 B aligned (s_bias is read as float4)
   float* s_bias = s_stats + kEpiWarps * (BN / 2);            // [BN] bias of the current N tile
+  float* s_sc2 = s_bias + BN;                                // EPI only: [BN] scale2, [BN] shift2 of the N tile
+  float* s_sh2 = s_sc2 + BN;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -572,6 +591,10 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
         for (int i = et; i < BN; i += kEpiThreads) {
           const int c = t.nt * BN + i;
           s_bias[i] = (p.bias != nullptr && c < p.n_total) ? __ldg(p.bias + c) : 0.f;
+          if constexpr (EPI) {
+            s_sc2[i] = (p.scale2 != nullptr && c < p.n_total) ? __ldg(p.scale2 + c) : 1.f;
+            s_sh2[i] = (p.shift2 != nullptr && c < p.n_total) ? __ldg(p.shift2 + c) : 0.f;
+          }
         }
         named_bar_sync(2, kEpiThreads);
         bias_nt = t.nt;
@@ -655,6 +678,12 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
             }
           }
         }
+        if constexpr (EPI) {
+          if (p.act != 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = act_apply(p.act, v[i], p.act_slope);
+          }
+        }
         if (do_stats) {
           float* dst = s_stats + ew * (BN / 2) + 2 * (c0 >> p.cpg_log2);
           if (p.cpg_log2 == 2) chunk_group_stats<8>(v, valid, lane, dst);
@@ -680,6 +709,26 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (j < 2 * nvec) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if constexpr (EPI) {
+            if (p.out2_h != nullptr) {
+              uint4* op = reinterpret_cast<uint4*>(p.out2_h + base + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j < nvec) {
+                  uint4 u;
+                  __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int i0 = 8 * j + 2 * e;
+                    const float a = act_apply(p.act2, fmaf(v[i0], s_sc2[c0 + i0], s_sh2[c0 + i0]), p.act_slope);
+                    const float b = act_apply(p.act2, fmaf(v[i0 + 1], s_sc2[c0 + i0 + 1], s_sh2[c0 + i0 + 1]), p.act_slope);
+                    h2[e] = __floats2half2_rn(a, b);
+                  }
+                  op[j] = u;
+                }
+              }
+            }
           }
         }
       }  // chunk loop
@@ -751,7 +800,7 @@ struct ConvCfg<128, true, true> {
   static constexpr int kMB = 2, kStages = 4;   // 4 x 41 KB halo boxes + 5 x 8 KB weight tiles
 };
 
-template <int BN, bool PAIR, bool HALO>
+template <int BN, bool PAIR, bool HALO, bool EPI = false>
 constexpr size_t conv_smem_bytes() {
   using Cfg = ConvCfg<BN, PAIR, HALO>;
   constexpr size_t b_bytes = static_cast<size_t>(PAIR ? BN / 2 : BN) * kBlockK * 2;
@@ -759,24 +808,24 @@ constexpr size_t conv_smem_bytes() {
   constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + (Cfg::kMB == 1 ? 6 : 5) * b_bytes
                                : Cfg::kStages * (Cfg::kMB * kABytes + b_bytes);
   return 1024 /*align slack*/ + ring + (3 * Cfg::kStages + 2 * kHaloBStagesMax + 4) * 8 + 16 +
-         kEpiWarps * (BN / 2) * 4 + BN * 4 + 64;
+         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + 64;
 }
 
-template <int BN, bool PAIR, bool HALO>
+template <int BN, bool PAIR, bool HALO, bool EPI = false>
 cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s) {
   using Cfg = ConvCfg<BN, PAIR, HALO>;
-  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, PAIR, HALO>;
+  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, PAIR, HALO, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(conv_smem_bytes<BN, PAIR, HALO>()));
+                                         static_cast<int>(conv_smem_bytes<BN, PAIR, HALO, EPI>()));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(HALO ? kConvThreadsHalo : kConvThreadsPlain);
-  cfg.dynamicSmemBytes = conv_smem_bytes<BN, PAIR, HALO>();
+  cfg.dynamicSmemBytes = conv_smem_bytes<BN, PAIR, HALO, EPI>();
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -795,7 +844,7 @@ int max_active_pairs() {
   using Cfg = ConvCfg<BN, true, HALO>;
   static int cached = -1;
   if (cached >= 0) return cached;
-  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, true, HALO>;
+  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, true, HALO, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(conv_smem_bytes<BN, true, HALO>()));
   cudaLaunchConfig_t cfg{};
@@ -823,6 +872,7 @@ struct wfk_conv_plan {
   int bn;
   int pair;
   int halo;
+  int epi;   // extended epilogue (activation / second activated output): EPI kernel variants
   int grid;
 };
 
@@ -929,7 +979,8 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   WFK_REQUIRE(d->taps_per_phase >= 1 && d->num_phases * d->taps_per_phase <= WFK_MAX_TAPS, "too many taps");
   WFK_REQUIRE(d->n_frames >= 1 && d->tile_h >= 1 && d->tile_w >= 1, "empty problem");
   WFK_REQUIRE(d->a[0].ptr != nullptr && d->b[0].ptr != nullptr, "A/B source 0 missing");
-  WFK_REQUIRE(d->out_h != nullptr || d->out_f != nullptr, "no output requested");
+  WFK_REQUIRE(d->out_h != nullptr || d->out_f != nullptr || d->out2_h != nullptr, "no output requested");
+  WFK_REQUIRE(d->act >= 0 && d->act <= WFK_ACT_SILU && d->act2 >= 0 && d->act2 <= WFK_ACT_SILU, "unknown activation");
   WFK_REQUIRE(d->ldc % 8 == 0, "ldc must be a multiple of 8");
   bool uses_src1 = false;
   for (int i = 0; i < d->num_phases * d->taps_per_phase; ++i) {
@@ -1010,6 +1061,17 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.out_sy = d->out_sy;
   p.out_sx = d->out_sx;
   p.ldc = d->ldc;
+  p.act = d->act;
+  p.act2 = d->act2;
+  p.act_slope = d->act_slope;
+  p.out2_h = static_cast<__half*>(d->out2_h);
+  p.scale2 = d->scale2;
+  p.shift2 = d->shift2;
+  plan->epi = (d->act != 0 || d->out2_h != nullptr) ? 1 : 0;
+  if (plan->epi && !plan->pair) {
+    delete plan;
+    return wfk::fail(WFK_ERR_INVALID, "activation epilogues need the CTA-pair kernels (WFK_CONV_PAIR=0 is set)");
+  }
   p.cpg_log2 = cpg_log2;
   p.groups_total = d->stats ? (d->n_total >> cpg_log2) : 0;
   p.idesc = wfk::umma_idesc_f16(plan->pair ? 256u : 128u, static_cast<uint32_t>(plan->bn), d->operand_bf16 ? 1u : 0u);
@@ -1055,7 +1117,14 @@ extern "C" int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream) {
   WFK_REQUIRE(plan != nullptr, "null plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (plan->halo) {
+  if (plan->epi) {
+    if (plan->halo)
+      e = (plan->bn == 256) ? wfk::launch_conv<256, true, true, true>(plan->params, plan->grid, s)
+                            : wfk::launch_conv<128, true, true, true>(plan->params, plan->grid, s);
+    else
+      e = (plan->bn == 256) ? wfk::launch_conv<256, true, false, true>(plan->params, plan->grid, s)
+                            : wfk::launch_conv<128, true, false, true>(plan->params, plan->grid, s);
+  } else if (plan->halo) {
     e = (plan->bn == 256) ? wfk::launch_conv<256, true, true>(plan->params, plan->grid, s)
                           : wfk::launch_conv<128, true, true>(plan->params, plan->grid, s);
   } else if (plan->pair) {

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const __half* _
                                                                  const float* __restrict__ bias,
                                                                  const float* __restrict__ post_w,
                                                                  const float* __restrict__ post_b,
-                                                                 float* __restrict__ out) {
+                                                                 float* __restrict__ out, int act) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const __half* _
 #pragma unroll
         for (int co = 0; co < COUT; ++co) r = (co == lane) ? acc[co] : r;
       }
+      if (act == WFK_ACT_SIGMOID) r = 1.f / (1.f + __expf(-r));  // nn.Sigmoid tail (ae_64x8x8_lin.py:85,105)
       out[(static_cast<int64_t>(fn) * COUT + lane) * hw + p] = r;
     }
   }
@@ -229,7 +230,14 @@ extern "C" int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int
 extern "C" int wfk_conv3x3_small_cout(const void* in, int n, int h, int w, int cin, const void* weight_h,
                                       const float* bias, int cout, const float* post_w, const float* post_b,
                                       float* out, void* stream) {
+  return wfk_conv3x3_small_cout_act(in, n, h, w, cin, weight_h, bias, cout, post_w, post_b, WFK_ACT_NONE, out, stream);
+}
+
+extern "C" int wfk_conv3x3_small_cout_act(const void* in, int n, int h, int w, int cin, const void* weight_h,
+                                          const float* bias, int cout, const float* post_w, const float* post_b,
+                                          int act, float* out, void* stream) {
   WFK_REQUIRE_INIT();
+  WFK_REQUIRE(act == WFK_ACT_NONE || act == WFK_ACT_SIGMOID, "act must be none or sigmoid");
   WFK_REQUIRE(in && weight_h && bias && out, "null pointer");
   WFK_REQUIRE(cin % 8 == 0 && cin > 0, "cin must be a multiple of 8");
   WFK_REQUIRE((post_w == nullptr) == (post_b == nullptr), "post_w / post_b must both be given or both NULL");
@@ -243,7 +251,7 @@ extern "C" int wfk_conv3x3_small_cout(const void* in, int n, int h, int w, int c
   const __half* wh = static_cast<const __half*>(weight_h);
 #define WFK_LAUNCH_SC(CO)                                                                                       \
   wfk::conv3x3_small_cout_kernel<CO><<<static_cast<unsigned>(blocks), 256, 0, s>>>(ih, n, h, w, cin, wh, bias, \
-                                                                                  post_w, post_b, out)
+                                                                                  post_w, post_b, out, act)
   switch (cout) {
     case 1: WFK_LAUNCH_SC(1); break;
     case 2: WFK_LAUNCH_SC(2); break;

@@ -236,3 +236,35 @@ def make_dlinear_case(variant: str, seed: int = 0, batch: int = 2, c: int = 4, h
     g = torch.Generator().manual_seed(_name_seed(f"dlinear.{variant}.lat", seed))
     lat = torch.randn((batch, INPUT_FRAMES + PRED_FRAMES, c, h, w), generator=g).float()
     return cfg, params, lat
+
+
+# ------------------------------------------------------------------------------------------------
+# NLayerDiscriminator (reference: pipeline/models/autoencoderkl/losses/model.py:100-150)
+def _normal(shape, name: str, seed: int, mean: float, std: float) -> torch.Tensor:
+    g = torch.Generator().manual_seed(_name_seed(name, seed))
+    return (torch.randn(shape, generator=g) * std + mean).float()
+
+
+def make_discriminator_state_dict(input_nc: int = 1, ndf: int = 64, n_layers: int = 3, seed: int = 0,
+                                  weight_std: float = 0.02) -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of ``NLayerDiscriminator(input_nc, ndf, n_layers)`` after ``.apply(weights_init)`` (conv
+    N(0, 0.02), BatchNorm weight N(1, 0.02), bias 0; losses/model.py:6-12) with NON-trivial running statistics,
+    so that eval-mode BatchNorm folding is exercised. ``weight_std`` can be raised for better-conditioned
+    parity cases (0.02-std weights shrink the activations layer by layer)."""
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["main.0.weight"] = _normal((ndf, input_nc, 4, 4), "disc.main.0.weight", seed, 0.0, weight_std * 4)
+    sd["main.0.bias"] = _uniform((ndf,), "disc.main.0.bias", seed, 0.25)
+    idx, mult = 2, 1
+    for n in range(1, n_layers + 1):
+        prev, mult = mult, min(2 ** n, 8)
+        cin, cout = ndf * prev, ndf * mult
+        sd[f"main.{idx}.weight"] = _normal((cout, cin, 4, 4), f"disc.main.{idx}.weight", seed, 0.0, weight_std)
+        sd[f"main.{idx + 1}.weight"] = _normal((cout,), f"disc.main.{idx + 1}.weight", seed, 1.0, 0.02)
+        sd[f"main.{idx + 1}.bias"] = _normal((cout,), f"disc.main.{idx + 1}.bias", seed, 0.0, 0.05)
+        sd[f"main.{idx + 1}.running_mean"] = _normal((cout,), f"disc.main.{idx + 1}.running_mean", seed, 0.0, 0.05)
+        sd[f"main.{idx + 1}.running_var"] = _uniform((cout,), f"disc.main.{idx + 1}.running_var", seed, 0.02) + 0.05
+        sd[f"main.{idx + 1}.num_batches_tracked"] = torch.tensor(10, dtype=torch.long)
+        idx += 3
+    sd[f"main.{idx}.weight"] = _normal((1, ndf * mult, 1, 1), f"disc.main.{idx}.weight", seed, 0.0, 0.05)
+    sd[f"main.{idx}.bias"] = _uniform((1,), f"disc.main.{idx}.bias", seed, 0.1)
+    return sd
