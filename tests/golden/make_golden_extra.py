@@ -123,6 +123,31 @@ def gen_discriminator(out):
             out[f"{tag}_hinge"] = np.array(d_loss.item())
 
 
+POSAWARE_GAIN = 1.1   # keeps activations O(0.2-0.5) through the ~110 layers and the sigmoid unsaturated
+
+
+def posaware_inputs(n=2, seed=51):
+    u8 = S.make_vil_sequences(n, 128, 128, 1, seed=seed)
+    return ((1 / 255) * u8.float()).permute(0, 3, 1, 2).contiguous()
+
+
+def posaware_state_dict():
+    from weatherforecastingtoolkit_b200.models.ae_64x8x8_lin import PosAwareAE_TF as Mine
+    return S.fill_state_dict(Mine(), "posaware", 0, gain=POSAWARE_GAIN)
+
+
+def gen_posaware(out):
+    from pipeline.models.ae_64x8x8_lin import PosAwareAE_TF
+    sd = posaware_state_dict()
+    m = PosAwareAE_TF().eval()
+    m.load_state_dict(sd, strict=True)
+    x = posaware_inputs()
+    with torch.no_grad():
+        y, z = m(x)
+    out["posaware_latent"] = z.numpy()
+    out["posaware_recon"] = y.numpy()
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     out = {}
@@ -133,7 +158,7 @@ def main():
     print("wrote extra_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
-EXTRA_GENERATORS = [gen_discriminator]
+EXTRA_GENERATORS = [gen_discriminator, gen_posaware]
 
 if __name__ == "__main__":
     main()

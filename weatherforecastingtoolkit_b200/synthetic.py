@@ -268,3 +268,36 @@ def make_discriminator_state_dict(input_nc: int = 1, ndf: int = 64, n_layers: in
     sd[f"main.{idx}.weight"] = _normal((1, ndf * mult, 1, 1), f"disc.main.{idx}.weight", seed, 0.0, 0.05)
     sd[f"main.{idx}.bias"] = _uniform((1,), f"disc.main.{idx}.bias", seed, 0.1)
     return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# PosAwareAE_TF / AE_ViT_2048: name-keyed random parameters over a module's own state_dict surface
+def fill_state_dict(module, prefix: str, seed: int = 0, gain: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
+    """Deterministic, well-conditioned random parameters for every entry of ``module.state_dict()`` (keys and
+    shapes come from the module, which mirrors the reference's): conv / linear weights uniform with bound
+    gain*sqrt(3/fan_in) (unit-gain, so activations keep their scale through ~100 layers), biases small,
+    BatchNorm / LayerNorm weights 1 +- 0.1, biases +- 0.1, running_mean +- 0.1, running_var in [0.8, 1.2],
+    embeddings N(0, 1) * 0.5. The same dict loads into the unmodified reference module (golden fixtures)."""
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, t in module.state_dict().items():
+        shp = tuple(t.shape)
+        leaf = name.rsplit(".", 1)[-1]
+        tag = f"{prefix}.{name}"
+        if leaf == "num_batches_tracked":
+            sd[name] = torch.tensor(10, dtype=torch.long)
+        elif leaf == "running_mean":
+            sd[name] = _uniform(shp, tag, seed, 0.1)
+        elif leaf == "running_var":
+            sd[name] = _uniform(shp, tag, seed, 0.2) + 1.0
+        elif leaf in ("weight", "in_proj_weight") and len(shp) >= 2:
+            fan_in = int(np.prod(shp[1:]))
+            if "up.0" in name:            # ConvTranspose2d [cin, cout, 4, 4], stride 2: 4 taps per output pixel
+                fan_in = shp[0] * 4
+            sd[name] = _uniform(shp, tag, seed, gain * math.sqrt(3.0 / fan_in))
+        elif leaf == "weight":            # norm weights
+            sd[name] = _uniform(shp, tag, seed, 0.1) + 1.0
+        elif leaf in ("bias", "in_proj_bias"):
+            sd[name] = _uniform(shp, tag, seed, 0.1)
+        else:                             # pos_emb, pos_embed, query_vec, dec_queries
+            sd[name] = _normal(shp, tag, seed, 0.0, 0.5)
+    return sd
