@@ -259,6 +259,31 @@ int wfk_conv1x1_cout1(const void* in, int n, int h, int w, int cin, const float*
  * sums[1] += sum relu(1 - x), sums[2] += sum relu(1 + x) over count values (double, caller-zeroed). */
 int wfk_logit_sums(const float* x, int64_t count, double* sums, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * a18  Token-path kernels of AE_ViT_2048 (pipeline/models/ae_vit.py:84-162); the dense linears run on
+ * wfk_conv_plan_* GEMMs.
+ *
+ * Conv2d(1, D, 16, 16) / ConvTranspose2d(D, 1, 16, 16) as GEMMs over 16x16 patches (ae_vit.py:100, 135,
+ * 141-143, 158-159): img [n, 1, h, w] fp32 <-> rows [n*(h/16)*(w/16)][256] (fp16 for patchify, fp32 for
+ * unpatchify), element (r, s) of a patch at column r*16 + s. */
+int wfk_patchify16(const float* img, int n, int h, int w, void* rows_h, void* stream);
+int wfk_unpatchify16(const float* rows_f, int n, int h, int w, float* img, void* stream);
+/* nn.MultiheadAttention core (ae_vit.py:106-111, 127-132): qkv [n*tokens][3*d_model] fp16 (q | k | v, heads are
+ * contiguous 64-wide slices) -> out [n*tokens][d_model] fp16 = softmax(q k^T / 8) v per (image, head).
+ * tokens <= 64, d_model = heads * 64. */
+int wfk_mha_small(const void* qkv, int n, int tokens, int d_model, int heads, void* out, void* stream);
+/* GlobalCrossEncode core (ae_vit.py:23-41): q_scaled [heads][d_latent/heads] fp32 = q_proj(query_vec) * scale
+ * (input independent); kv [n*tokens][2*d_latent] fp16 (k | v) -> out [n][d_latent] fp16. */
+int wfk_cross_encode_attn(const float* q_scaled, const void* kv, int n, int tokens, int d_latent, int heads,
+                          void* out, void* stream);
+/* nn.LayerNorm(d, eps) over rows of an fp32 matrix (the post-norm residual sums, ae_vit.py:106-111):
+ * out_h fp16 and / or out_f fp32. */
+int wfk_layernorm_rows(const float* x, int64_t rows, int d, const float* gamma, const float* beta, float eps,
+                       void* out_h, float* out_f, void* stream);
+/* out[b, l, :] = vec[b, :] + pos[l, :] (fp32 in, fp16 out): GlobalCrossDecode with a single key/value token
+ * (ae_vit.py:44-82: softmax over one key is exactly 1) followed by + pos_embed (ae_vit.py:152). */
+int wfk_bcast_add_rows(const float* vec, const float* pos, int n, int tokens, int d, void* out, void* stream);
+
 /* Decoder tail, fused: GroupNorm(groups, eps) + SiLU + conv3x3(c -> 1, pad 1).  Replaces
  * conv_norm_out + conv_act + conv_out of Decoder.forward (vae.py:162-164).  x: [n, h, w, c] fp16 raw
  * stream; stats as wfk_groupnorm_apply; weight: [9][c] fp32 (tap-major); out: [n, 1, h, w] fp32. */

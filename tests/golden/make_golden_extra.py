@@ -148,6 +148,35 @@ def gen_posaware(out):
     out["posaware_recon"] = y.numpy()
 
 
+def vit_inputs(n=2, seed=61):
+    u8 = S.make_vil_sequences(n, 128, 128, 1, seed=seed)
+    return ((1 / 255) * u8.float()).permute(0, 3, 1, 2).contiguous()
+
+
+def vit_state_dict():
+    from weatherforecastingtoolkit_b200.models.ae_vit import AE_ViT_2048 as Mine
+    return S.fill_state_dict(Mine(), "vit", 0, gain=1.0)
+
+
+def gen_vit(out):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):      # the reference module builds a model and prints at import
+        from pipeline.models.ae_vit import AE_ViT_2048
+    sd = vit_state_dict()
+    m = AE_ViT_2048().eval()
+    m.load_state_dict(sd, strict=True)
+    x = vit_inputs()
+    with torch.no_grad():
+        y, lat = m(x)
+        # token-sequence latent [B, 64, 512] (BASELINE config 4): the encoder stack's output, ae_vit.py:141-145
+        z = m.patch_embed(x).flatten(2).transpose(1, 2) + m.pos_embed
+        z = m.encoder(z)
+    out["vit_recon"] = y.numpy()
+    out["vit_latent"] = lat.numpy()
+    out["vit_tokens"] = z.numpy()
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     out = {}
@@ -158,7 +187,7 @@ def main():
     print("wrote extra_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
-EXTRA_GENERATORS = [gen_discriminator, gen_posaware]
+EXTRA_GENERATORS = [gen_discriminator, gen_posaware, gen_vit]
 
 if __name__ == "__main__":
     main()
