@@ -239,7 +239,7 @@ def run_b200_arm(args):
     barrier()
 
     # ---- timed region 1: inputs resident in HBM
-    timer = engine.KernelTimer()
+    timer = engine.KernelTimer(all_ops=bool(args.breakdown))
     engine.TIMER = timer
     sampler = ClockSampler(local_rank)
     launches0 = _cabi.launch_count()

@@ -185,6 +185,14 @@ typedef struct wfk_conv_desc {
   int32_t operand_bf16;  /* 0: fp16 operands (default), 1: bf16 operands                        */
   const void* gn_table;  /* optional fused GroupNorm+SiLU on A source 0 (3x3 stride-1 convs only):
                             [n_frames][cin] float2 (scale, shift) from wfk_gn_table, or NULL          */
+  /* Alternative to gn_table: derive (scale, shift) inside the kernel from the producer's raw statistics
+   * (same arithmetic as wfk_gn_table; no separate launch). gn_stats: [n_frames][gn_groups][2] double (sum, sum of
+   * squares over cin/gn_groups channels x tile_h*tile_w pixels); gamma, beta: [cin]. */
+  const double* gn_stats;
+  const float* gn_gamma;
+  const float* gn_beta;
+  float gn_eps;
+  int32_t gn_groups;
   /* Extended epilogue (eval-mode BatchNorm folded into weights/bias by the caller):
    *   v = act(D + bias (+ residual))            -> out_h / out_f / stats
    *   out2_h = act2(scale2[c] * v + shift2[c])  -> a second fp16 tensor, same addressing as out_h
@@ -221,6 +229,13 @@ int wfk_gn_table(const double* stats, const float* gamma, const float* beta, int
 int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int w, const float* pre_w,
                           const float* pre_b, const float* weight, const float* bias, int cout, void* out,
                           double* stats, int cpg, void* stream);
+
+/* The same layers on the tensor cores (mma.sync m16n8k16, fp16 operands / fp32 accumulate): K = (cin + ones_plane)
+ * * 9 <= 48. weight_h: [ceil(K/16)*16][cout] fp16, row k = ci*9 + tap, zero rows beyond K; with ones_plane != 0 an
+ * extra constant-one input plane (1 inside the image, 0 in the padding) carries the bias of a 1x1 convolution folded
+ * in front (post_quant_conv, autoencoder_kl.py:87). cout a multiple of 128; cpg 4, 8 or 16 when stats != NULL. */
+int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w, int ones_plane, const void* weight_h,
+                        const float* bias, int cout, void* out, double* stats, int cpg, void* stream);
 
 /* Direct 3x3 (pad 1, stride 1) convolution for tiny output-channel counts, optional post 1x1.
  * Replaces decoder.conv_out (vae.py:148) and encoder.conv_out + quant_conv (vae.py:68,
@@ -295,6 +310,10 @@ int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const float* gamm
  * Replaces torch.softmax(attention_scores.float(), dim=-1) (attention.py:171); `scale` is the
  * baddbmm alpha (attention.py:148, 168). */
 int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, void* stream);
+
+/* [n, hw, c] fp32 -> [n, c, hw] fp32: the conv-GEMM's NHWC result to the model-facing NCHW moments tensor
+ * (AutoencoderKL.encode returns [B, 2*latent_channels, h, w], autoencoder_kl.py:80-84). */
+int wfk_nhwc_to_nchw_f32(const float* in, int n, int hw, int c, float* out, void* stream);
 
 /* fp32 -> fp16 conversion of weights at pack time (device to device). */
 int wfk_f32_to_f16(const float* in, int64_t n, void* out, void* stream);

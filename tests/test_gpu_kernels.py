@@ -162,3 +162,71 @@ def test_metrics_deterministic(lib):
     a = M.metric_partials(p.to(DEV), t.to(DEV))
     b = M.metric_partials(p.to(DEV), t.to(DEV))
     assert np.array_equal(a.ints, b.ints) and np.array_equal(a.floats, b.floats)
+
+
+# ------------------------------------------------------------------ row softmax (attention.py:171)
+@pytest.mark.parametrize("rows,cols", [(37, 2304), (5, 4096), (9, 50), (3, 4100)])
+def test_softmax_rows(lib, rows, cols):
+    from weatherforecastingtoolkit_b200 import _cabi
+    torch.manual_seed(rows + cols)
+    s = torch.randn(rows, cols, device=DEV) * 7.0
+    out = torch.empty(rows, cols, dtype=torch.float16, device=DEV)
+    scale = 1.0 / math.sqrt(512)
+    _cabi.check(lib.wfk_softmax_rows(s.data_ptr(), rows, cols, scale, out.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream), "softmax")
+    want = torch.softmax(s.float().cpu() * scale, dim=-1)
+    assert (out.float().cpu() - want).abs().max().item() < 1e-3   # fp16 output
+    assert (out.float().sum(-1).cpu() - 1).abs().max().item() < 2e-3
+
+
+def test_nhwc_to_nchw_f32(lib):
+    from weatherforecastingtoolkit_b200 import _cabi
+    x = torch.randn(3, 5, 7, 8, device=DEV)
+    out = torch.empty(3, 8, 5, 7, device=DEV)
+    _cabi.check(lib.wfk_nhwc_to_nchw_f32(x.data_ptr(), 3, 5 * 7, 8, out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "transpose")
+    assert torch.equal(out, x.permute(0, 3, 1, 2).contiguous())
+
+
+# ------------------------------------------------------------------ tensor-core stem convolutions
+@pytest.mark.parametrize("n,cin,h,w,cout,ones,cpg", [(2, 1, 64, 64, 128, 0, 4), (1, 1, 50, 70, 128, 0, 4),
+                                                      (2, 4, 48, 48, 512, 1, 16), (1, 4, 13, 9, 256, 1, 8),
+                                                      (1, 3, 20, 24, 128, 0, 8)])
+def test_stem_tc_vs_conv2d(lib, n, cin, h, w, cout, ones, cpg):
+    """wfk_conv3x3_stem_tc == conv3x3(pad 1) of (optionally) a 1x1 pre-convolution, on identical fp16 operands;
+    GroupNorm sums of the fp32 result."""
+    from weatherforecastingtoolkit_b200 import _cabi
+    torch.manual_seed(n * 1000 + h * 10 + cin)
+    x = torch.rand(n, cin, h, w)
+    wt = torch.randn(cout, cin, 3, 3) / math.sqrt(9 * cin)
+    bias = torch.randn(cout) * 0.1
+    if ones:
+        pw, pb = torch.randn(cin, cin) * 0.5, torch.randn(cin) * 0.3
+        wk = torch.cat([torch.einsum("oirs,ij->ojrs", wt, pw), torch.einsum("oirs,i->ors", wt, pb).unsqueeze(1)], 1)
+    else:
+        wk = wt
+    kk = wk.shape[1] * 9
+    wp = torch.zeros((kk + 15) // 16 * 16, cout)
+    wp[:kk] = wk.permute(1, 2, 3, 0).reshape(kk, cout)
+    wp16 = wp.half()
+    out = torch.empty(n, h, w, cout, dtype=torch.float16, device=DEV)
+    groups = cout // cpg
+    stats = torch.zeros(n, groups, 2, dtype=torch.float64, device=DEV)
+    xd, wd, bd = x.to(DEV), wp16.to(DEV), bias.to(DEV)
+    _cabi.check(lib.wfk_conv3x3_stem_tc(xd.data_ptr(), n, cin, h, w, ones, wd.data_ptr(), bd.data_ptr(), cout,
+                                        out.data_ptr(), stats.data_ptr(), cpg, torch.cuda.current_stream().cuda_stream), "stem")
+    # reference on the SAME rounded operands: fp16 input planes (+ the ones plane), fp16 packed weights
+    planes = x.half().float()
+    if ones:
+        planes = torch.cat([planes, torch.ones(n, 1, h, w)], 1)
+    wref = wp16.float()[:kk].reshape(wk.shape[1], 3, 3, cout).permute(3, 0, 1, 2).contiguous()
+    want = F.conv2d(planes, wref, bias, padding=1).permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), want) < 2e-3
+    torch.cuda.synchronize()
+    ws = want.reshape(n, h * w, groups, cpg).double()
+    assert torch.allclose(stats[..., 0].cpu(), ws.sum(dim=(1, 3)), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(stats[..., 1].cpu(), (ws * ws).sum(dim=(1, 3)), rtol=1e-3, atol=5e-2)
+    if ones:  # against the unfolded fp32 definition: conv3x3(zero-padded (1x1 conv of x))
+        z = F.conv2d(x, pw.reshape(cin, cin, 1, 1), pb)
+        want32 = F.conv2d(z, wt, bias, padding=1).permute(0, 2, 3, 1)
+        assert rel_l2(out.float(), want32) < 5e-3

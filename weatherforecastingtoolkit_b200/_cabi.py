@@ -54,6 +54,8 @@ class ConvDesc(C.Structure):
         ("out_rows", C.c_int32), ("out_cols", C.c_int32), ("out_sy", C.c_int32), ("out_sx", C.c_int32),
         ("ldc", C.c_int32), ("cpg", C.c_int32), ("operand_bf16", C.c_int32),
         ("gn_table", C.c_void_p),
+        ("gn_stats", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p), ("gn_eps", C.c_float),
+        ("gn_groups", C.c_int32),
         ("act", C.c_int32), ("act2", C.c_int32), ("act_slope", C.c_float),
         ("out2_h", C.c_void_p), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
     ]
@@ -86,6 +88,8 @@ _PROTOTYPES = {
                                C.c_void_p, C.c_void_p]),
     "wfk_conv3x3_small_cin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "wfk_conv3x3_stem_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "wfk_conv3x3_small_cout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wfk_conv3x3_small_cout_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -106,6 +110,7 @@ _PROTOTYPES = {
     "wfk_gn_silu_conv3x3_c1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "wfk_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "wfk_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wfk_f32_to_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 

@@ -55,6 +55,14 @@ struct ConvKernelParams {
   int seg1_slab;       // HALO: weight slab of the shortcut
   const float2* gn_table;  // HALO: [frame][cin] (scale, shift) of a fused GroupNorm+SiLU on source 0, or null
   int gn_cin;
+  // HALO, alternative to gn_table: the (scale, shift) pairs are derived inside the kernel from the producer's raw
+  // statistics, which removes one tiny kernel launch (and its pipeline bubble) in front of every fused convolution
+  const double* gn_stats;  // [frame][gn_groups][2] (sum, sum of squares)
+  const float* gn_gamma;
+  const float* gn_beta;
+  double gn_inv_count;     // 1 / (channels per group * pixels)
+  float gn_eps;
+  int gn_cpg_log2, gn_groups;
   int wait_hint_ns; // >0: epilogue / producer waits park with this try_wait suspend hint
   int xform_debug;  // experiment switch: 1 = load/store without math, 2 = skip the transform entirely
   int num_phases, taps_per_phase;
@@ -236,6 +244,11 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap
+  // the tail of the previous kernel in the stream; nothing below touches global memory before that kernel has
+  // completed and flushed. The trigger lets the NEXT kernel's CTAs take over SMs as this grid's CTAs retire.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int total_tiles = p.num_phases * p.n_frames * p.tiles_y * p.tiles_x * p.tiles_n;
   const int tile0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
@@ -461,7 +474,9 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
                                t.frame * p.b_frame_mul;
               mbar_wait_h(&bempty_bar[bstage], bphase ^ 1u, p.wait_hint_ns);
               uint8_t* sbt = smem_b + bstage * kBBytes;
-              if (PAIR) {
+              if (PAIR && p.xform_debug == 8) {   // timing experiment: no weight traffic at all (results are garbage)
+                if (leader) mbar_arrive(&bfull_bar[bstage]);
+              } else if (PAIR) {
                 if (leader) mbar_arrive_expect_tx(&bfull_bar[bstage], 2 * kBBytes);
                 tma_load_3d_2sm(sbt, bm, &bfull_bar[bstage], kb * kBlockK,
                                 t.nt * BN + static_cast<int>(cta_rank) * kBRows, slab);
@@ -496,18 +511,53 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
       auto step = [&](const int seg, const int kb) {
         
           mbar_wait_h(&full_bar[stage], phase, p.wait_hint_ns);
-          if (seg == 0 && p.gn_table != nullptr && p.xform_debug != 2) {
+          if (seg == 0 && (p.gn_table != nullptr || p.gn_stats != nullptr) && p.xform_debug != 2) {
             float ga[8], gb[8];
+            if (p.gn_stats != nullptr) {
+              // same arithmetic as wfk_gn_table: mean / rstd per group in double, (a, b) = (rstd*gamma, beta - mean*a)
+              const int c0 = kb * kBlockK + lc * 8;
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + c0));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + c0 + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + c0));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + c0 + 4));
+              const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              const double* st = p.gn_stats + static_cast<int64_t>(t.frame) * p.gn_groups * 2;
+              float mean_f[2], rstd_f[2];
+              const int gfirst = c0 >> p.gn_cpg_log2;
+              const int ng = (p.gn_cpg_log2 == 2) ? 2 : 1;   // 8 channels span two groups only when cpg == 4
+#pragma unroll
+              for (int gi = 0; gi < 2; ++gi) {
+                if (gi < ng) {
+                  const double mean = st[(gfirst + gi) * 2 + 0] * p.gn_inv_count;
+                  double var = st[(gfirst + gi) * 2 + 1] * p.gn_inv_count - mean * mean;
+                  var = var < 0.0 ? 0.0 : var;
+                  mean_f[gi] = static_cast<float>(mean);
+                  rstd_f[gi] = static_cast<float>(rsqrt(var + static_cast<double>(p.gn_eps)));
+                } else {
+                  mean_f[gi] = mean_f[0];
+                  rstd_f[gi] = rstd_f[0];
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int gi = (p.gn_cpg_log2 == 2) ? (j >> 2) : 0;
+                const float a = rstd_f[gi] * gam[j];
+                // silu(z) = h + h*tanh(h) with h = z/2: one MUFU op per element instead of two (ex2 + rcp)
+                ga[j] = 0.5f * a;
+                gb[j] = 0.5f * (bet[j] - mean_f[gi] * a);
+              }
+            } else {
             const float4* tp = reinterpret_cast<const float4*>(p.gn_table + static_cast<int64_t>(t.frame) * p.gn_cin +
                                                                kb * kBlockK + lc * 8);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 v = __ldg(tp + j);
-              // silu(z) = h + h*tanh(h) with h = z/2: one MUFU op per element instead of two (ex2 + rcp)
               ga[2 * j] = 0.5f * v.x;
               gb[2 * j] = 0.5f * v.y;
               ga[2 * j + 1] = 0.5f * v.z;
               gb[2 * j + 1] = 0.5f * v.w;
+            }
             }
             // Software-pipelined: each thread owns rows (xt>>3) + 16*i of the box; the loads of kXfGroup rows are
             // issued back to back (explicit ld.shared: independent of the stores of the previous group), then
@@ -827,13 +877,16 @@ cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s
   cfg.blockDim = dim3(HALO ? kConvThreadsHalo : kConvThreadsPlain);
   cfg.dynamicSmemBytes = conv_smem_bytes<BN, PAIR, HALO, EPI>();
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const bool pdl = !(std::getenv("WFK_PDL") && std::getenv("WFK_PDL")[0] == '0');
+  cfg.numAttrs = pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, params);
 }
 
@@ -1043,9 +1096,27 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.seg1_slab = slab1;
   p.gn_table = static_cast<const float2*>(d->gn_table);
   p.gn_cin = static_cast<int>(d->a[0].dim[0]);
+  p.gn_stats = d->gn_stats;
+  p.gn_gamma = d->gn_gamma;
+  p.gn_beta = d->gn_beta;
+  p.gn_eps = d->gn_eps;
+  p.gn_groups = d->gn_groups;
+  p.gn_cpg_log2 = 0;
+  p.gn_inv_count = 0.0;
+  if (d->gn_stats != nullptr) {
+    const int cin = static_cast<int>(d->a[0].dim[0]);
+    const int cpg_in = (d->gn_groups > 0 && cin % d->gn_groups == 0) ? cin / d->gn_groups : 0;
+    const int l2 = ilog2_exact(cpg_in);
+    if (d->gn_gamma == nullptr || d->gn_beta == nullptr || l2 < 2 || d->gn_table != nullptr) {
+      delete plan;
+      return wfk::fail(WFK_ERR_INVALID, "gn_stats needs gamma, beta, >= 4 (power of two) channels per group and no gn_table");
+    }
+    p.gn_cpg_log2 = l2;
+    p.gn_inv_count = 1.0 / (static_cast<double>(cpg_in) * d->tile_h * d->tile_w);
+  }
   p.wait_hint_ns = std::getenv("WFK_WAIT_HINT") ? std::atoi(std::getenv("WFK_WAIT_HINT")) : 0;
   p.xform_debug = std::getenv("WFK_XFORM_DEBUG") ? std::atoi(std::getenv("WFK_XFORM_DEBUG")) : 0;
-  if (d->gn_table != nullptr && !plan->halo) {
+  if ((d->gn_table != nullptr || d->gn_stats != nullptr) && !plan->halo) {
     delete plan;
     return wfk::fail(WFK_ERR_INVALID, "a fused GroupNorm+SiLU input (gn_table) needs a HALO-eligible 3x3 stride-1 convolution");
   }

@@ -118,6 +118,61 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   for (int i = threadIdx.x; i < cols; i += blockDim.x) dst[i] = __float2half_rn(s_row[i] * inv);
 }
 
+// Same for cols % 4 == 0 and cols <= 4096: the row lives in registers (up to 4 float4 per thread), one 128-bit
+// load and one 64-bit store per 4 elements, two block reductions. HBM-bound: 6 bytes per score.
+__global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __restrict__ scores, int cols, float scale,
+                                                               __half* __restrict__ probs) {
+  __shared__ float s_red[2][8];
+  const int64_t r = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(scores + r * cols);
+  const int nvec = cols >> 2;
+  float4 v[4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < nvec) {
+      float4 t = __ldcs(src + i);   // streamed once
+      t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale;
+      v[k] = t;
+      m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+    }
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_red[0][threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = s_red[0][0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[0][i]);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < nvec) {
+      v[k].x = __expf(v[k].x - m); v[k].y = __expf(v[k].y - m); v[k].z = __expf(v[k].z - m); v[k].w = __expf(v[k].w - m);
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s_red[1][threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += s_red[1][i];
+  const float inv = 1.f / sum;
+  uint2* dst = reinterpret_cast<uint2*>(probs + r * cols);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < nvec) {
+      uint2 u;
+      *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[k].x * inv, v[k].y * inv);
+      *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[k].z * inv, v[k].w * inv);
+      dst[i] = u;
+    }
+  }
+}
+
 // (scale, shift) per (frame, channel) of a GroupNorm, for consumers that fuse the apply step.
 __global__ void gn_table_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int hw, int c, int groups, float eps,
@@ -134,6 +189,17 @@ __global__ void gn_table_kernel(const double* __restrict__ stats, const float* _
     const float a = rstd * gamma[ch];
     table[static_cast<int64_t>(n) * c + ch] = make_float2(a, beta[ch] - static_cast<float>(mean) * a);
   }
+}
+
+// [n, hw, c] fp32 -> [n, c, hw] fp32 (the model-facing layout of the moments tensor)
+__global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int64_t total, int hw, int c,
+                                        float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // index into out
+  if (i >= total) return;
+  const int p = static_cast<int>(i % hw);
+  const int ch = static_cast<int>((i / hw) % c);
+  const int64_t n = i / (static_cast<int64_t>(hw) * c);
+  out[i] = in[(n * hw + p) * c + ch];
 }
 
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, int64_t n, __half* __restrict__ out) {
@@ -173,9 +239,23 @@ extern "C" int wfk_softmax_rows(const float* scores, int64_t rows, int cols, flo
   WFK_REQUIRE_INIT();
   WFK_REQUIRE(scores && probs, "null pointer");
   WFK_REQUIRE(rows > 0 && rows < (1ll << 31) && cols > 0 && cols <= 11264, "unsupported softmax shape");
+  if (cols % 4 == 0 && cols <= 4096) {
+    wfk::softmax_rows_vec_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        scores, cols, scale, static_cast<__half*>(probs));
+    return wfk::launched("softmax_rows_vec_kernel");
+  }
   wfk::softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, cols * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       scores, cols, scale, static_cast<__half*>(probs));
   return wfk::launched("softmax_rows_kernel");
+}
+
+extern "C" int wfk_nhwc_to_nchw_f32(const float* in, int n, int hw, int c, float* out, void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(in && out && n > 0 && hw > 0 && c > 0, "bad argument");
+  const int64_t total = static_cast<int64_t>(n) * hw * c;
+  wfk::nhwc_to_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, total, hw, c, out);
+  return wfk::launched("nhwc_to_nchw_f32_kernel");
 }
 
 extern "C" int wfk_f32_to_f16(const float* in, int64_t n, void* out, void* stream) {

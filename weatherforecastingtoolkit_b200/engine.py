@@ -31,8 +31,9 @@ class KernelTimer:
     called after a synchronize. ``flops`` are NOMINAL (2*M*N*K of the reference layer), not what the
     sub-pixel decomposition actually executes."""
 
-    def __init__(self):
+    def __init__(self, all_ops: bool = False):
         self.records = []  # (what, nominal_flops, start_event, end_event)
+        self.all_ops = all_ops  # also time the non-GEMM kernels (bench.py --breakdown)
 
     def record(self, what, flops, start, end):
         self.records.append((what, flops, start, end))
@@ -40,6 +41,8 @@ class KernelTimer:
     def summary(self):
         tot_ms, tot_flops, n = 0.0, 0.0, 0
         for _, fl, s, e in self.records:
+            if not fl:
+                continue
             tot_ms += s.elapsed_time(e)
             tot_flops += fl
             n += 1
@@ -106,9 +109,39 @@ class PackedAKL:
                 if mod == "encoder.conv_in" or mod == "decoder.conv_in":
                     # direct kernel: [cin*9][cout] fp32
                     self.t[mod + ".w_direct"] = w.permute(1, 2, 3, 0).reshape(cin * 9, cout).contiguous()
+                    # tensor-core stem kernel: [K padded to 16][cout] fp16, row k = ci*9 + tap. For the decoder the
+                    # 1x1 post_quant_conv in front (autoencoder_kl.py:87) is folded in (fp32): W_eff[:, cj] = sum_ci
+                    # W[:, ci] pq_w[ci, cj]; its bias rides on a constant-one plane (present only where a tap is inside
+                    # the image, exactly like the reference's zero padding AFTER post_quant_conv)
+                    wk = w
+                    if mod == "decoder.conv_in" and "post_quant_conv.weight" in sd:
+                        pw = sd["post_quant_conv.weight"].detach().to(device=device, dtype=torch.float32)
+                        pw = pw.reshape(pw.shape[0], pw.shape[1])
+                        pb = sd["post_quant_conv.bias"].detach().to(device=device, dtype=torch.float32)
+                        wk = torch.cat([torch.einsum("oirs,ij->ojrs", w, pw), torch.einsum("oirs,i->ors", w, pb).unsqueeze(1)], 1)
+                    kk = wk.shape[1] * 9
+                    if kk <= 48:
+                        wp = torch.zeros((kk + 15) // 16 * 16, cout, dtype=torch.float32, device=device)
+                        wp[:kk] = wk.permute(1, 2, 3, 0).reshape(kk, cout)
+                        self.t[mod + ".w_tc"] = wp.to(F16).contiguous()
                 elif mod == "encoder.conv_out" or mod == "decoder.conv_out":
                     # direct kernel: [cout][9][cin] fp16
                     self.t[mod + ".w_direct"] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin).contiguous().to(F16)
+                    if mod == "encoder.conv_out" and "quant_conv.weight" in sd:
+                        # quant_conv (1x1, autoencoder_kl.py:82) folded behind conv_out in fp32:
+                        # Wq (Wc * x + bc) + bq = (Wq Wc) * x + (Wq bc + bq); rows padded to a multiple of 8
+                        wq = sd["quant_conv.weight"].detach().to(device=device, dtype=torch.float32)
+                        wq = wq.reshape(wq.shape[0], wq.shape[1])
+                        bq = sd["quant_conv.bias"].detach().to(device=device, dtype=torch.float32)
+                        bc = sd["encoder.conv_out.bias"].detach().to(device=device, dtype=torch.float32)
+                        wf = torch.einsum("oc,cirs->oirs", wq, w)
+                        npad = (cout + 7) // 8 * 8
+                        wp = torch.zeros(9, npad, cin, dtype=torch.float32, device=device)
+                        wp[:, :cout] = wf.permute(2, 3, 0, 1).reshape(9, cout, cin)
+                        bp = torch.zeros(npad, dtype=torch.float32, device=device)
+                        bp[:cout] = wq @ bc + bq
+                        self.t[mod + ".w_folded"] = wp.to(F16).contiguous()
+                        self.t[mod + ".bias_folded"] = bp.contiguous()
                     if cout == 1:  # fused GroupNorm+SiLU+conv tail: [9][cin] fp32
                         self.t[mod + ".w_tap"] = w.permute(0, 2, 3, 1).reshape(9, cin).contiguous()
                 elif ".upsamplers." in mod:
@@ -188,6 +221,8 @@ class AKLEngine:
         import os
         self.fuse_gn = (os.environ.get("WFK_FUSE_GN", "1") != "0" and os.environ.get("WFK_CONV_HALO", "1") != "0"
                         and os.environ.get("WFK_CONV_PAIR", "1") != "0")
+        self.gn_inline = os.environ.get("WFK_GN_INLINE", "1") != "0"  # (scale, shift) derived inside the conv kernel
+        self.stem_tc = os.environ.get("WFK_STEM_TC", "1") != "0"   # tensor-core stem kernels (A/B switch)
         self._plans: Dict[Tuple, "_Program"] = {}
         self._keep: List = []
 
@@ -249,7 +284,7 @@ class _Program:
         self.stats_arena.zero_()
         timer = TIMER
         for fn, args, what, flops in self.ops:
-            if timer is not None and flops:
+            if timer is not None and (flops or timer.all_ops):
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
                 _cabi.check(fn(*args, stream), what)
@@ -318,9 +353,18 @@ class _Program:
                    self.eng.groups, GN_EPS, tab.data_ptr()), what)
         return tab
 
+    def _gn_inline(self, d: ConvDesc, x: _Act, pname: str):
+        """GroupNorm(pname) + SiLU of the conv's input computed from x's raw statistics inside the kernel."""
+        t = self.eng.w.t
+        d.gn_stats = x.stats.data_ptr()
+        d.gn_gamma = t[pname + ".weight"].data_ptr()
+        d.gn_beta = t[pname + ".bias"].data_ptr()
+        d.gn_eps = GN_EPS
+        d.gn_groups = self.eng.groups
+
     def conv3x3(self, x: _Act, wname: str, bias: torch.Tensor, cout: int, residual: Optional[torch.Tensor] = None,
                 shortcut: Optional[Tuple[torch.Tensor, str]] = None, want_stats=True, what="conv3x3",
-                gn_tab: Optional[torch.Tensor] = None) -> _Act:
+                gn_tab: Optional[torch.Tensor] = None, gn_from: Optional[str] = None) -> _Act:
         """3x3 stride-1 pad-1 conv (+bias, +residual | fused 1x1 shortcut) -> new activation. With ``gn_tab`` the
         input is the RAW tensor and GroupNorm+SiLU is applied while it is staged in shared memory."""
         n, h, w, cin = x.shape
@@ -347,6 +391,8 @@ class _Program:
         d.a_frame_mul, d.b_frame_mul = 1, 0
         self._epilogue(d, bias, residual, out, None, stats, h, w, cout)
         d.gn_table = _ptr(gn_tab)
+        if gn_from is not None:
+            self._gn_inline(d, x, gn_from)
         k_total = 9 * cin + (shortcut[0].shape[3] if shortcut is not None else 0)
         self._conv_plan(d, what, 2.0 * n * h * w * cout * k_total)
         return _Act(out, stats)
@@ -423,6 +469,17 @@ class _Program:
         cout = t[p + ".conv1.bias"].numel()
         if self.eng.fuse_gn and x.shape[1] >= 2:
             # GroupNorm apply + SiLU fused into the convs' halo staging: no normalised copies in HBM
+            if self.eng.gn_inline:
+                h1 = self.conv3x3(x, p + ".conv1.w", t[p + ".conv1.bias"], cout, what=p + ".gn1+conv1", gn_from=p + ".norm1")
+                if (p + ".conv_shortcut.w") in t:
+                    out = self.conv3x3(h1, p + ".conv2.w", t[p + ".conv2.bias_sc"], cout, shortcut=(x.t, p + ".conv_shortcut.w"),
+                                       what=p + ".gn2+conv2+shortcut", gn_from=p + ".norm2")
+                else:
+                    out = self.conv3x3(h1, p + ".conv2.w", t[p + ".conv2.bias"], cout, residual=x.t,
+                                       what=p + ".gn2+conv2+res", gn_from=p + ".norm2")
+                self.pool.put(h1.t)
+                self.pool.put(x.t)
+                return out
             t1 = self.gn_table(x, p + ".norm1", what=p + ".norm1(table)")
             h1 = self.conv3x3(x, p + ".conv1.w", t[p + ".conv1.bias"], cout, what=p + ".gn1+conv1", gn_tab=t1)
             t2 = self.gn_table(h1, p + ".norm2", what=p + ".norm2(table)")
@@ -544,10 +601,16 @@ class _Program:
         c0 = eng.boc[0]
         s0 = self.pool.get((n, H, W, c0))
         st = self._new_stats()
-        self._add(self.lib.wfk_conv3x3_small_cin,
-                  (self.input.data_ptr(), n, cin, H, W, None, None, t["encoder.conv_in.w_direct"].data_ptr(),
-                   t["encoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
-                  "encoder.conv_in")
+        if eng.stem_tc and "encoder.conv_in.w_tc" in t and c0 % 128 == 0 and (c0 // eng.groups) in (4, 8, 16):
+            self._add(self.lib.wfk_conv3x3_stem_tc,
+                      (self.input.data_ptr(), n, cin, H, W, 0, t["encoder.conv_in.w_tc"].data_ptr(),
+                       t["encoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
+                      "encoder.conv_in")
+        else:
+            self._add(self.lib.wfk_conv3x3_small_cin,
+                      (self.input.data_ptr(), n, cin, H, W, None, None, t["encoder.conv_in.w_direct"].data_ptr(),
+                       t["encoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
+                      "encoder.conv_in")
         x = _Act(s0, st)
         for i in range(nb):
             for j in range(eng.lpb):
@@ -558,10 +621,36 @@ class _Program:
                 self.pool.put(x.t)
                 x = y
         x = self.mid(x, "encoder.mid_block")
-        a = self.gn(x, "encoder.conv_norm_out", what="encoder.conv_norm_out")
-        self.pool.put(x.t)
         _, h, w, c = x.shape
         out = torch.empty((n, 2 * eng.lc, h, w), dtype=torch.float32, device=self.dev)
+        if eng.fuse_gn and h >= 2 and "encoder.conv_out.w_folded" in t:
+            # conv_norm_out + SiLU fused into the halo staging, conv_out (+ folded quant_conv) on the tensor cores
+            # (N padded to 8: a sliver of a 128-wide tile, still 5x faster than the CUDA-core gather), fp32 NHWC
+            # result transposed to the NCHW moments tensor
+            tab = None if eng.gn_inline else self.gn_table(x, "encoder.conv_norm_out", what="encoder.conv_norm_out(table)")
+            npad = t["encoder.conv_out.bias_folded"].numel()
+            mom = self.pool.get((n, h, w, npad), torch.float32)
+            d = ConvDesc()
+            self._view_nhwc(d.a[0], x.t, n, h, w, c)
+            self._view_w(d.b[0], t["encoder.conv_out.w_folded"], c, npad, 9)
+            d.n_frames, d.tile_h, d.tile_w, d.n_total = n, h, w, npad
+            d.num_phases, d.taps_per_phase = 1, 9
+            for r in range(3):
+                for s_ in range(3):
+                    d.taps[r * 3 + s_] = Tap(s_ - 1, r - 1, 0, 0, 0, r * 3 + s_, c // 64, 0)
+            d.a_frame_mul, d.b_frame_mul = 1, 0
+            self._epilogue(d, t["encoder.conv_out.bias_folded"], None, None, mom, None, h, w, npad)
+            d.gn_table = _ptr(tab)
+            if eng.gn_inline:
+                self._gn_inline(d, x, "encoder.conv_norm_out")
+            self._conv_plan(d, "encoder.gn+conv_out+quant_conv", 2.0 * n * h * w * (2 * eng.lc) * 9 * c)
+            if npad != 2 * eng.lc:
+                raise ValueError("moments channel count must be a multiple of 8 for the tensor-core tail")
+            self._add(self.lib.wfk_nhwc_to_nchw_f32, (mom.data_ptr(), n, h * w, npad, out.data_ptr()), "moments->NCHW")
+            self.keep.append((x.t, mom, tab))
+            return out
+        a = self.gn(x, "encoder.conv_norm_out", what="encoder.conv_norm_out")
+        self.pool.put(x.t)
         self._add(self.lib.wfk_conv3x3_small_cout,
                   (a.data_ptr(), n, h, w, c, t["encoder.conv_out.w_direct"].data_ptr(),
                    t["encoder.conv_out.bias"].data_ptr(), 2 * eng.lc, t["quant_conv.w"].data_ptr(),
@@ -578,11 +667,17 @@ class _Program:
         c0 = rev[0]
         s0 = self.pool.get((n, h, w, c0))
         st = self._new_stats()
-        self._add(self.lib.wfk_conv3x3_small_cin,
-                  (self.input.data_ptr(), n, lc, h, w, t["post_quant_conv.w"].data_ptr(),
-                   t["post_quant_conv.bias"].data_ptr(), t["decoder.conv_in.w_direct"].data_ptr(),
-                   t["decoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
-                  "post_quant_conv+decoder.conv_in")
+        if eng.stem_tc and "decoder.conv_in.w_tc" in t and c0 % 128 == 0 and (c0 // eng.groups) in (4, 8, 16):
+            self._add(self.lib.wfk_conv3x3_stem_tc,
+                      (self.input.data_ptr(), n, lc, h, w, 1, t["decoder.conv_in.w_tc"].data_ptr(),
+                       t["decoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
+                      "post_quant_conv+decoder.conv_in")
+        else:
+            self._add(self.lib.wfk_conv3x3_small_cin,
+                      (self.input.data_ptr(), n, lc, h, w, t["post_quant_conv.w"].data_ptr(),
+                       t["post_quant_conv.bias"].data_ptr(), t["decoder.conv_in.w_direct"].data_ptr(),
+                       t["decoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
+                      "post_quant_conv+decoder.conv_in")
         x = _Act(s0, st)
         x = self.mid(x, "decoder.mid_block")
         for i in range(nb):
