@@ -338,11 +338,13 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0 && leader) {
+    if (leader) {
       // ------------------------------------------------------------ MMA issuer (leader CTA only when PAIR)
-      // The issue loop must sustain one tcgen05.mma per 64 tensor-core cycles (N = 128), so descriptors
-      // are built incrementally: the high word (SBO, version, swizzle) is constant, the low word is the
-      // stage's start address >> 4 plus (bytes >> 4) per K slice / pixel block.
+      // The whole warp runs this warp-uniform loop (waits included); one elected lane issues the tcgen05
+      // instructions. The loop must sustain one tcgen05.mma per 64 tensor-core cycles (N = 128), so descriptors
+      // are built incrementally: the high word (SBO, version, swizzle) is constant, the low word is the stage's
+      // start address >> 4 plus (bytes >> 4) per K slice / pixel block.
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -368,21 +370,21 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
           auto step = [&](const int seg, const int kb) {
             const int ntaps = seg == 0 ? p.taps_per_phase : 1;
             const uint32_t a_hi = seg == 0 ? a_hi0 : a_hi1;
-            
-              mbar_wait(&ready_bar[stage], phase);
+            mbar_wait(&ready_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
+            for (int ti = 0; ti < ntaps; ++ti) {
+              int r = 0, sx = 0;  // source 1: the box starts at the block origin
+              if (seg == 0) {
+                const wfk_tap tap = p.taps[t.phase * p.taps_per_phase + ti];
+                r = tap.dy + 1;
+                sx = tap.dx + 1;
+              }
+              mbar_wait(&bfull_bar[bstage], bphase);
               tc_fence_after();
-              const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
-              for (int ti = 0; ti < ntaps; ++ti) {
-                int r = 0, sx = 0;  // source 1: the box starts at the block origin
-                if (seg == 0) {
-                  const wfk_tap tap = p.taps[t.phase * p.taps_per_phase + ti];
-                  r = tap.dy + 1;
-                  sx = tap.dx + 1;
-                }
-                mbar_wait(&bfull_bar[bstage], bphase);
-                tc_fence_after();
-                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(bstage) * (kBBytes >> 4);
-                const uint32_t a_tap = a_lo + static_cast<uint32_t>((r * kHaloPitch + sx) * 8);  // rows * 128 B >> 4
+              const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(bstage) * (kBBytes >> 4);
+              const uint32_t a_tap = a_lo + static_cast<uint32_t>((r * kHaloPitch + sx) * 8);  // rows * 128 B >> 4
+              if (issuer) {
                 // the 4 K slices of one pixel block are issued back to back (same accumulator)
 #pragma unroll
                 for (int mb = 0; mb < MB; ++mb) {
@@ -394,25 +396,33 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
                     else umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, (k > 0) ? 1u : accumulate);
                   }
                 }
-                accumulate = 1;
                 if (PAIR) umma_commit_2sm(&bempty_bar[bstage]);
                 else umma_commit(&bempty_bar[bstage]);
-                if (++bstage == kBStages) {
-                  bstage = 0;
-                  bphase ^= 1u;
-                }
               }
+              __syncwarp();
+              accumulate = 1;
+              if (++bstage == kBStages) {
+                bstage = 0;
+                bphase ^= 1u;
+              }
+            }
+            if (issuer) {
               if (PAIR) umma_commit_2sm(&empty_bar[stage]);
               else umma_commit(&empty_bar[stage]);
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1u;
-              }
-            };
+            }
+            __syncwarp();
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          };
           for (int i0 = 0; i0 < p.seg_kblocks[0]; ++i0) step(0, i0);
           for (int j1 = 0; j1 < p.seg_kblocks[1]; ++j1) step(1, j1);
-          if (PAIR) umma_commit_2sm(&tfull_bar[acc]);
-          else umma_commit(&tfull_bar[acc]);
+          if (issuer) {
+            if (PAIR) umma_commit_2sm(&tfull_bar[acc]);
+            else umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1u;
         }
@@ -430,29 +440,36 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
           tc_fence_after();
           const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * (kStageBytes >> 4);
           const uint32_t b_lo = a_lo + ((MB * kABytes) >> 4);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-              const uint64_t adesc =
-                  (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + static_cast<uint32_t>(mb * (kABytes >> 4) + 2 * k));
-              if (PAIR) umma_f16_2sm(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
-              else umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, accumulate);
+              for (int mb = 0; mb < MB; ++mb) {
+                const uint64_t adesc =
+                    (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + static_cast<uint32_t>(mb * (kABytes >> 4) + 2 * k));
+                // accumulate turns on after EVERY pixel block has issued its first (overwriting) MMA
+                if (PAIR) umma_f16_2sm(d_tmem + mb * BN, adesc, bdesc, idesc, (k > 0) ? 1u : accumulate);
+                else umma_f16(d_tmem + mb * BN, adesc, bdesc, idesc, (k > 0) ? 1u : accumulate);
+              }
             }
-            accumulate = 1;  // after EVERY pixel block has issued its first (overwriting) MMA
+            // frees the smem slot (in both CTAs when PAIR) once these MMAs have read it
+            if (PAIR) umma_commit_2sm(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
           }
-          // frees the smem slot (in both CTAs when PAIR) once these MMAs have read it
-          if (PAIR) umma_commit_2sm(&empty_bar[stage]);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
+          accumulate = 1;
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
         // accumulator complete -> epilogue(s)
-        if (PAIR) umma_commit_2sm(&tfull_bar[acc]);
-        else umma_commit(&tfull_bar[acc]);
+        if (issuer) {
+          if (PAIR) umma_commit_2sm(&tfull_bar[acc]);
+          else umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }

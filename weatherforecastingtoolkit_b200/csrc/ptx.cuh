@@ -164,6 +164,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n, ui
 }
 
 // ------------------------------------------------------------------ misc
+// One lane of a converged warp (always the same lane for a full mask). Used by the MMA issuer: the WHOLE warp runs
+// the (warp-uniform) issue loop so that ptxas keeps descriptors / addresses in uniform registers, and only the
+// tcgen05 instructions themselves are predicated on this lane. Entering the loop under `if (lane == 0)` instead made
+// every descriptor a divergent value: ptxas then emitted ELECT + 5 x R2UR per tcgen05.mma and the single issuing
+// thread -- not the tensor pipe -- bounded the kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // explicit shared-state-space 16-byte accesses (a generic LD/ST through a casted pointer is slower and the
 // compiler must assume it aliases every other generic access)
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {

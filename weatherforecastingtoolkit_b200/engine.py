@@ -221,7 +221,10 @@ class AKLEngine:
         import os
         self.fuse_gn = (os.environ.get("WFK_FUSE_GN", "1") != "0" and os.environ.get("WFK_CONV_HALO", "1") != "0"
                         and os.environ.get("WFK_CONV_PAIR", "1") != "0")
-        self.gn_inline = os.environ.get("WFK_GN_INLINE", "1") != "0"  # (scale, shift) derived inside the conv kernel
+        # (scale, shift) derived inside the conv kernel instead of a wfk_gn_table launch. Off by default: once the MMA
+        # issue loop stopped being the bottleneck the halo transform became co-critical, and the per-K-block fp64
+        # mean / rstd arithmetic in its warps cost 17 % of the step (233 vs 280 frames/s)
+        self.gn_inline = os.environ.get("WFK_GN_INLINE", "0") != "0"
         self.stem_tc = os.environ.get("WFK_STEM_TC", "1") != "0"   # tensor-core stem kernels (A/B switch)
         self._plans: Dict[Tuple, "_Program"] = {}
         self._keep: List = []
