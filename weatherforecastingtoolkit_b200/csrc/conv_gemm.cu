@@ -35,8 +35,23 @@ constexpr int kBlockK = 64;  // fp16 elements = one 128 B swizzle row
 constexpr int kEpiWarps = 8;  // two per TMEM lane quarter: latency hiding by TLP
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kConvThreadsPlain = 64 + kEpiThreads;   // warps: TMA, MMA, 8 epilogue
-constexpr int kXformWarps = 4;                         // HALO: GroupNorm+SiLU applied in place to the staged halo
-constexpr int kConvThreadsHalo = 96 + 32 * kXformWarps + kEpiThreads;  // warps: TMA(A), MMA, TMA(B), 4 transform, 8 epilogue
+// HALO: GroupNorm+SiLU applied in place to the staged halo by 4 (MB = 1) or 8 (MB = 2) transform warps. The MB = 2
+// kernel (Cout = 128 layers at 384^2) stages 324 halo rows per 64-channel K block against the same 4608 tensor-core
+// cycles as the MB = 1 kernel's 180 rows: with 4 warps the transform, not the tensor pipe, bounded those layers.
+// 8 transform + 8 epilogue + 4 (TMA-B, TMA-A, MMA, idle) warps = 640 threads only fit the register file because the
+// roles trade registers with setmaxnreg (warpgroup-aligned roles: transform 72, epilogue 136, producers / MMA 56).
+__host__ __device__ constexpr int xform_warps(bool halo, int mb) { return halo ? (mb == 2 ? 8 : 4) : 0; }
+__host__ __device__ constexpr int conv_threads(bool halo, int mb) {
+  return halo ? (mb == 2 ? 640 : 96 + 32 * 4 + kEpiThreads) : kConvThreadsPlain;
+}
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 constexpr int kABytes = kBlockM * kBlockK * 2;
 // HALO mode (3x3 stride-1 taps): pixel blocks are 8 wide x 16 tall; ONE (8*MB+2) x 18 pixel halo box per
 // 64-channel K block serves all taps through shifted A descriptors (tcgen05's 128B swizzle is a pure
@@ -166,8 +181,10 @@ __device__ __forceinline__ void chunk_group_stats(const float (&v)[32], bool val
 }
 
 template <int BN, int MB, int STAGES, bool PAIR, bool HALO, bool EPI>
-__global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1)
+__global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
     conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  constexpr int kXformWarps = xform_warps(HALO, MB);
+  constexpr bool kRegSplit = HALO && MB == 2;      // 20 warps: per-role register budgets via setmaxnreg
   constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
   constexpr int kBBytes = kBRows * kBlockK * 2;
   constexpr int kCtas = PAIR ? 2 : 1;
@@ -178,9 +195,9 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
   constexpr int kHaloStage = (kHaloBytes + 1023) & ~1023;
   // halo transform: 128 threads = 16 row slots x 8 sixteen-byte chunks; kXfPasses row passes per box, the loads of
   // kXfGroup passes in flight per thread (MB=2: 324 rows -> 21 = 3 x 7 passes; MB=1: 180 rows -> 12 = 2 x 6)
-  constexpr int kXfPasses = (kHaloPitch * kHaloRows + 15) / 16;
-  constexpr int kXfGroup = (MB == 2) ? 7 : 6;
-  static_assert(kXfPasses % kXfGroup == 0, "transform passes must split into whole groups");
+  constexpr int kXfRowsPerPass = HALO ? 4 * kXformWarps : 16;  // 8 threads (16-byte chunks) per 128-byte row
+  constexpr int kXfPasses = (kHaloPitch * kHaloRows + kXfRowsPerPass - 1) / kXfRowsPerPass;
+  constexpr int kXfGroup = 6;                      // loads in flight per thread (MB=2: 11 passes = 6 + 5; MB=1: 12 = 6 + 6)
   constexpr int kStageBytes = HALO ? kHaloStage : MB * kABytes + kBBytes;
   constexpr int kBStages = HALO ? (MB == 1 ? 6 : 5) : 0;  // weight-tile ring depth (16 KB / 8 KB tiles)
   // Warp roles by warp id. The SM's warp arbiter favours HIGHER warp ids, so the latency-critical
@@ -188,6 +205,7 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
   // TMA,) activation TMA, then the MMA issuer last. The epilogue outranks the transform: with K = 9*128
   // it is co-critical with the MMAs, whereas a halo transform has nine taps' worth of slack.
   // (Measured: for the 256-wide tiles the opposite order of these two is ~3 % faster, so it depends on MB.)
+  // MB = 2 (kRegSplit): transform 0..7 | epilogue 8..15 | TMA-B 16, TMA-A 17, MMA 18, idle 19 (whole warpgroups per role)
   constexpr int kXformWarp0 = (MB == 2) ? 0 : kEpiWarps;
   constexpr int kFirstEpiWarp = (HALO && MB == 2) ? kXformWarps : 0;
   constexpr int kWarpTmaB = HALO ? kEpiWarps + kXformWarps : -1;
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
   const int bw = 1 << p.bw_log2;
   const int bh = kBlockM >> p.bw_log2;
 
-  if (warp == kWarpTmaA) {
+  auto role_tma_a = [&]() {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
@@ -337,7 +355,8 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
         }
       }
     }
-  } else if (warp == kWarpMma) {
+  };
+  auto role_mma = [&]() {
     if (leader) {
       // ------------------------------------------------------------ MMA issuer (leader CTA only when PAIR)
       // The whole warp runs this warp-uniform loop (waits included); one elected lane issues the tcgen05
@@ -474,7 +493,8 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (HALO && warp == kWarpTmaB) {
+  };
+  auto role_tma_b = [&]() {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer for the weight tiles (HALO)
       int bstage = 0;
@@ -511,7 +531,8 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
         for (int j1 = 0; j1 < p.seg_kblocks[1]; ++j1) step(1, j1);
       }
     }
-  } else if (HALO && warp >= kXformWarp0 && warp < kXformWarp0 + kXformWarps) {
+  };
+  auto role_xform = [&]() {
     // -------------------------------------------------------------- halo transform (HALO, warps 3..6)
     // GroupNorm apply + SiLU of the consumer's input, fused: y = silu(a[c]*x + b[c]) in place on the staged
     // halo (once per element, reused by all nine taps). Pixels outside the image stay the zeros TMA wrote
@@ -583,17 +604,17 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
             const uint32_t sa = smem_u32(smem + stage * kStageBytes);
             const int row0 = xt >> 3;
 #pragma unroll 1
-            for (int g0 = 0; g0 < kXfPasses; g0 += kXfGroup) {
+            for (int g0 = 0; g0 < kXfPasses; g0 += kXfGroup) {   // the last group may be partial: `ok` bounds the rows
               uint4 u[kXfGroup];
               uint32_t addr[kXfGroup];
               bool ok[kXfGroup];
 #pragma unroll
               for (int j = 0; j < kXfGroup; ++j) {
-                const int row = row0 + 16 * (g0 + j);
+                const int row = row0 + kXfRowsPerPass * (g0 + j);
                 const int hy = row / kHaloPitch, hx = row - hy * kHaloPitch;
                 const int py = y0 + hy, px = x0 + hx;
                 // zero padding stays zero: out-of-image pixels are skipped
-                ok[j] = (row < kHaloPitch * kHaloRows) && py >= 0 && py < p.tile_h && px >= 0 && px < p.tile_w;
+                ok[j] = (g0 + j < kXfPasses) && (row < kHaloPitch * kHaloRows) && py >= 0 && py < p.tile_h && px >= 0 && px < p.tile_w;
                 addr[j] = sa + static_cast<uint32_t>(row * 128 + ((lc ^ (row & 7)) << 4));
                 if (ok[j]) u[j] = lds_v4(addr[j]);
               }
@@ -634,7 +655,8 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
       for (int i0 = 0; i0 < p.seg_kblocks[0]; ++i0) step(0, i0);
       for (int j1 = 0; j1 < p.seg_kblocks[1]; ++j1) step(1, j1);
     }
-  } else {
+  };
+  auto role_epi = [&]() {
     // -------------------------------------------------------------- epilogue (8 warps)
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
     const int et = threadIdx.x - 32 * kFirstEpiWarp;  // 0..kEpiThreads-1
@@ -701,6 +723,19 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
         }
       };
       if (part < total_it) issue_residual(part);
+      // The residual tensor was written a layer or two ago and has long left L2: pull this tile's rows into L2 now,
+      // a whole MMA phase before they are needed, so that the chunk-ahead register prefetch above only has to cover
+      // an L2 hit instead of an HBM round trip (which made the "+residual" layers epilogue-bound).
+      if (has_res) {
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          if ((MB == 1 || (mb & (kParts - 1)) == part) && valid_mb[mb]) {
+            const char* rp = reinterpret_cast<const char*>(p.residual + base_mb[mb]);
+            for (int off = (MB == 1 ? part * 128 : 0); off < ncols * 2; off += (MB == 1 ? kParts * 128 : 128))
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+          }
+        }
+      }
       mbar_wait_h(&tfull_bar[acc], acc_phase, p.wait_hint_ns);
       tc_fence_after();
       const uint32_t tlane =
@@ -827,6 +862,28 @@ __global__ void __launch_bounds__(HALO ? kConvThreadsHalo : kConvThreadsPlain, 1
         named_bar_sync(1, kEpiThreads);
       }
     }
+  };
+
+  if constexpr (kRegSplit) {
+    // whole warpgroups per role; each group first trades registers (the launch allocation is 96 per thread)
+    if (warp >= kWarpTmaB) {
+      setmaxnreg_dec<56>();
+      if (warp == kWarpTmaA) role_tma_a();
+      else if (warp == kWarpMma) role_mma();
+      else if (warp == kWarpTmaB) role_tma_b();
+    } else if (warp < kXformWarp0 + kXformWarps) {
+      setmaxnreg_dec<72>();
+      role_xform();
+    } else {
+      setmaxnreg_inc<136>();
+      role_epi();
+    }
+  } else {
+    if (warp == kWarpTmaA) role_tma_a();
+    else if (warp == kWarpMma) role_mma();
+    else if (HALO && warp == kWarpTmaB) role_tma_b();
+    else if (HALO && warp >= kXformWarp0 && warp < kXformWarp0 + kXformWarps) role_xform();
+    else role_epi();
   }
 
   tc_fence_before();
@@ -891,7 +948,7 @@ cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(HALO ? kConvThreadsHalo : kConvThreadsPlain);
+  cfg.blockDim = dim3(conv_threads(HALO, Cfg::kMB));
   cfg.dynamicSmemBytes = conv_smem_bytes<BN, PAIR, HALO, EPI>();
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
@@ -919,7 +976,7 @@ int max_active_pairs() {
                        static_cast<int>(conv_smem_bytes<BN, true, HALO>()));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(g_num_sms);
-  cfg.blockDim = dim3(HALO ? kConvThreadsHalo : kConvThreadsPlain);
+  cfg.blockDim = dim3(conv_threads(HALO, Cfg::kMB));
   cfg.dynamicSmemBytes = conv_smem_bytes<BN, true, HALO>();
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
