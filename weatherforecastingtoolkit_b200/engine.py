@@ -225,9 +225,17 @@ class AKLEngine:
         # issue loop stopped being the bottleneck the halo transform became co-critical, and the per-K-block fp64
         # mean / rstd arithmetic in its warps cost 17 % of the step (233 vs 280 frames/s)
         self.gn_inline = os.environ.get("WFK_GN_INLINE", "0") != "0"
+        self.res_as_mma = os.environ.get("WFK_RES_AS_MMA", "1") != "0"
         self.stem_tc = os.environ.get("WFK_STEM_TC", "1") != "0"   # tensor-core stem kernels (A/B switch)
         self._plans: Dict[Tuple, "_Program"] = {}
         self._keep: List = []
+
+    def identity_weight(self, c: int) -> str:
+        """Name of a [1][c][c] fp16 identity matrix in the packed-weight table (residual add as a 1x1 MMA tap)."""
+        name = f"identity{c}.w"
+        if name not in self.w.t:
+            self.w.t[name] = torch.eye(c, dtype=F16, device=self.device).unsqueeze(0).contiguous()
+        return name
 
     # ------------------------------------------------------------------ public
     def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
@@ -367,7 +375,8 @@ class _Program:
 
     def conv3x3(self, x: _Act, wname: str, bias: torch.Tensor, cout: int, residual: Optional[torch.Tensor] = None,
                 shortcut: Optional[Tuple[torch.Tensor, str]] = None, want_stats=True, what="conv3x3",
-                gn_tab: Optional[torch.Tensor] = None, gn_from: Optional[str] = None) -> _Act:
+                gn_tab: Optional[torch.Tensor] = None, gn_from: Optional[str] = None,
+                count_shortcut_flops: bool = True) -> _Act:
         """3x3 stride-1 pad-1 conv (+bias, +residual | fused 1x1 shortcut) -> new activation. With ``gn_tab`` the
         input is the RAW tensor and GroupNorm+SiLU is applied while it is staged in shared memory."""
         n, h, w, cin = x.shape
@@ -396,7 +405,8 @@ class _Program:
         d.gn_table = _ptr(gn_tab)
         if gn_from is not None:
             self._gn_inline(d, x, gn_from)
-        k_total = 9 * cin + (shortcut[0].shape[3] if shortcut is not None else 0)
+        # nominal work of the REFERENCE layer: an identity "shortcut" that carries the residual add is not counted
+        k_total = 9 * cin + (shortcut[0].shape[3] if (shortcut is not None and count_shortcut_flops) else 0)
         self._conv_plan(d, what, 2.0 * n * h * w * cout * k_total)
         return _Act(out, stats)
 
@@ -489,6 +499,13 @@ class _Program:
             if (p + ".conv_shortcut.w") in t:
                 out = self.conv3x3(h1, p + ".conv2.w", t[p + ".conv2.bias_sc"], cout,
                                    shortcut=(x.t, p + ".conv_shortcut.w"), what=p + ".gn2+conv2+shortcut", gn_tab=t2)
+            elif self.eng.res_as_mma and cout == 128 and cin == cout:
+                # Cout = 128 layers are epilogue-bound with a residual (two chunks of loads, converts and adds per
+                # accumulator chunk): feed the skip connection through the tensor cores instead, as a fused 1x1
+                # "shortcut" with identity weights (exact: 1.0 * x accumulates in fp32), +11 % MMA work
+                out = self.conv3x3(h1, p + ".conv2.w", t[p + ".conv2.bias"], cout,
+                                   shortcut=(x.t, self.eng.identity_weight(cout)), what=p + ".gn2+conv2+res(mma)", gn_tab=t2,
+                                   count_shortcut_flops=False)
             else:
                 out = self.conv3x3(h1, p + ".conv2.w", t[p + ".conv2.bias"], cout, residual=x.t,
                                    what=p + ".gn2+conv2+res", gn_tab=t2)
