@@ -49,7 +49,7 @@ def main():
         t = eng.w.t
         t["tmp.w"] = wt.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().half()
         if mode == "plain":
-            hs.conv3x3(_Act(x, None), "tmp.w", bias, cout)
+            hs.conv3x3(_Act(x, None), "tmp.w", bias, cout, want_stats=not os.environ.get("NOSTATS"))
         elif mode == "residual":
             res = torch.randn(n, hw, hw, cout, device=dev).half()
             hs.conv3x3(_Act(x, None), "tmp.w", bias, cout, residual=res)

@@ -39,7 +39,8 @@ constexpr int kConvThreadsPlain = 64 + kEpiThreads;   // warps: TMA, MMA, 8 epil
 // kernel (Cout = 128 layers at 384^2) stages 324 halo rows per 64-channel K block against the same 4608 tensor-core
 // cycles as the MB = 1 kernel's 180 rows: with 4 warps the transform, not the tensor pipe, bounded those layers.
 // 8 transform + 8 epilogue + 4 (TMA-B, TMA-A, MMA, idle) warps = 640 threads only fit the register file because the
-// roles trade registers with setmaxnreg (warpgroup-aligned roles: transform 72, epilogue 136, producers / MMA 56).
+// roles trade registers with setmaxnreg (warpgroup-aligned roles: transform 64, epilogue 144, producers / MMA 56:
+// 8*64 + 8*144 + 4*56 = 1888 <= 20*96 -- setmaxnreg.inc draws only on registers the CTA's own warps released).
 __host__ __device__ constexpr int xform_warps(bool halo, int mb) { return halo ? (mb == 2 ? 8 : 4) : 0; }
 __host__ __device__ constexpr int conv_threads(bool halo, int mb) {
   return halo ? (mb == 2 ? 640 : 96 + 32 * 4 + kEpiThreads) : kConvThreadsPlain;
@@ -180,11 +181,33 @@ __device__ __forceinline__ void chunk_group_stats(const float (&v)[32], bool val
   }
 }
 
+// Transposing warp reduction: every lane holds 32 partial values; afterwards lane L holds the warp-wide total of the
+// value whose index is returned (31 shuffles for 32 x 32 partials instead of 160 for 32 separate xor reductions).
+__device__ __forceinline__ int warp_transpose_reduce32(float (&v)[32], int lane) {
+  int idx = 0;
+#pragma unroll
+  for (int n = 32, off = 16; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+    idx += upper ? (n >> 1) : 0;
+#pragma unroll
+    for (int i = 0; i < (n >> 1); ++i) {
+      const float keep = upper ? v[i + (n >> 1)] : v[i];
+      const float send = upper ? v[i] : v[i + (n >> 1)];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return idx;
+}
+
 template <int BN, int MB, int STAGES, bool PAIR, bool HALO, bool EPI>
 __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
     conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr int kXformWarps = xform_warps(HALO, MB);
   constexpr bool kRegSplit = HALO && MB == 2;      // 20 warps: per-role register budgets via setmaxnreg
+  // Row-contiguous (shared-memory staged) epilogue accesses: pays for the 128-wide tiles, whose K = 9*128 layers are
+  // epilogue / LSU-bound; the 256-wide tiles keep direct row-per-lane accesses (their epilogue has 2-4x the MMA time
+  // to hide in, and the extra staging traffic and the shallower operand ring cost more than the stores)
+  constexpr bool kCoalesce = (BN == 128);
   constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
   constexpr int kBBytes = kBRows * kBlockK * 2;
   constexpr int kCtas = PAIR ? 2 : 1;
@@ -226,6 +249,9 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
   float* s_bias = s_stats + kEpiWarps * (BN / 2);            // [BN] bias of the current N tile
   float* s_sc2 = s_bias + BN;                                // EPI only: [BN] scale2, [BN] shift2 of the N tile
   float* s_sh2 = s_sc2 + BN;
+  // per-epilogue-warp staging tile (32 rows x 64 B, 16-byte units XOR-swizzled): turns the row-per-lane register
+  // layout of a TMEM chunk into row-contiguous global accesses
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + BN * (EPI ? 3 : 1));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -672,9 +698,53 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       for (int i = et; i < kEpiWarps * (BN / 2); i += kEpiThreads) s_stats[i] = 0.f;
       named_bar_sync(1, kEpiThreads);
     }
+    // fixed-order fold of the epilogue warps' partials in s_stats, then one fp64 reduction per (group, moment)
+    auto fold_stats = [&](const int frame, const int nt) {
+      named_bar_sync(1, kEpiThreads);
+      const int groups_in_tile = BN >> p.cpg_log2;
+      if (et < 2 * groups_in_tile) {
+        const int g = ((nt * BN) >> p.cpg_log2) + (et >> 1);
+        float tot = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < kEpiWarps; ++wi) {
+          tot += s_stats[wi * (BN / 2) + et];
+          s_stats[wi * (BN / 2) + et] = 0.f;
+        }
+        atomicAdd(&p.stats[(static_cast<int64_t>(frame) * p.groups_total + g) * 2 + (et & 1)], static_cast<double>(tot));
+      }
+      named_bar_sync(1, kEpiThreads);
+    };
+    // Cout = 128 kernel (kRegSplit, 4-channel groups): the (sum, sum of squares) partials of a thread's two chunk
+    // columns live in registers across all tiles of a frame; the cross-lane reduction, the shared-memory fold and its
+    // two block barriers run once per FRAME CHANGE (~4 tiles) instead of a shuffle butterfly per chunk and a fold per
+    // tile -- the epilogue, not the tensor pipe, bounded these K = 9*128 layers.
+    const bool reg_stats = kRegSplit && do_stats && p.cpg_log2 == 2 && p.tiles_n == 1;
+    float rs0[8], rq0[8], rs1[8], rq1[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) rs0[g] = rq0[g] = rs1[g] = rq1[g] = 0.f;
+    int stats_frame = -1;
+    auto flush_reg_stats = [&](const int frame) {
+      float vals[32];  // index = (slot * 8 + group) * 2 + moment
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        vals[2 * g] = rs0[g];
+        vals[2 * g + 1] = rq0[g];
+        vals[16 + 2 * g] = rs1[g];
+        vals[16 + 2 * g + 1] = rq1[g];
+        rs0[g] = rq0[g] = rs1[g] = rq1[g] = 0.f;
+      }
+      const int k = warp_transpose_reduce32(vals, lane);
+      const int slot = k >> 4, g = (k >> 1) & 7, m = k & 1;
+      s_stats[ew * (BN / 2) + 2 * (8 * (part + kParts * slot) + g) + m] = vals[0];
+      fold_stats(frame, 0);
+    };
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord t = decode_tile(p, tile);
       const int row = quarter * 32 + lane;
+      if (reg_stats && t.frame != stats_frame) {
+        if (stats_frame >= 0) flush_reg_stats(stats_frame);
+        stats_frame = t.frame;
+      }
       if (t.nt != bias_nt) {  // stage this N tile's bias once (smem broadcast reads in the chunk loop)
         named_bar_sync(2, kEpiThreads);
         for (int i = et; i < BN; i += kEpiThreads) {
@@ -707,19 +777,62 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       const int ncols = min(BN, p.n_total - t.nt * BN);  // N tail: columns >= ncols are padding
       const int nchunks = (ncols + 31) >> 5;
       const int total_it = MB * nchunks;
+      // Coalesced global accesses (fp16 output, fp16 residual): for access j a lane serves 16 bytes (unit lane & 3)
+      // of row 8*j + lane/4 of the warp's 32 rows, so one instruction covers 8 rows x 64 contiguous bytes instead of
+      // 32 rows x 16 bytes. A warp-wide 128-bit store that touches 32 different lines made the epilogue of the
+      // K = 9*128 layers LSU-bound (measured: +23 % with the stores removed, +30 % on residual layers).
+      int64_t cbase[MB][4];
+      uint32_t cvalid = 0;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int blk = static_cast<int>(cta_rank) * MB + mb;
+        const int bx = p.stack_x ? t.tx * kBlocksPerTile + blk : t.tx;
+        const int by = p.stack_x ? t.ty : t.ty * kBlocksPerTile + blk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = quarter * 32 + 8 * j + (lane >> 2);
+          const int py = by * bh + (rr >> p.bw_log2);
+          const int px = bx * bw + (rr & (bw - 1));
+          if (py < p.tile_h && px < p.tile_w) cvalid |= 1u << (mb * 4 + j);
+          const int oy = py * p.out_sy + (t.phase >> 1);
+          const int ox = px * p.out_sx + (t.phase & 1);
+          const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
+          cbase[mb][j] = pix * p.ldc + static_cast<int64_t>(t.nt) * BN + 8 * (lane & 3);
+        }
+      }
+      const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(ew) * 2048u;
+      // swizzled staging offsets: this lane's OWN row (unit j) and the coalesced (row 8j + lane/4, unit lane & 3) slots
+      const uint32_t own_row = stg + static_cast<uint32_t>(lane) * 64u;
+      const uint32_t own_x = static_cast<uint32_t>((lane >> 1) & 3);
+      uint32_t co_off[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t rr = 8u * j + (lane >> 2);
+        co_off[j] = stg + rr * 64u + ((static_cast<uint32_t>(lane & 3) ^ ((rr >> 1) & 3u)) << 4);
+      }
       // residual values are prefetched one chunk ahead (and before the accumulator is even ready) so
       // their global-memory latency is off the epilogue's critical path
       uint4 rnext[4];
       auto issue_residual = [&](int it) {
         const int mb_i = (MB == 1) ? 0 : (it >= nchunks ? 1 : 0);
         const int c0_i = (it - mb_i * nchunks) << 5;
-        const bool v_i = (MB == 1) ? valid_mb[0] : (mb_i ? valid_mb[1] : valid_mb[0]);
-        const int64_t b_i = (MB == 1) ? base_mb[0] : (mb_i ? base_mb[1] : base_mb[0]);
-        if (has_res && v_i) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + b_i + c0_i);
+        if constexpr (kCoalesce) {
+          if (has_res && c0_i + 8 * (lane & 3) < ncols) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (c0_i + 8 * j < ncols) rnext[j] = __ldg(rp + j);
+            for (int j = 0; j < 4; ++j) {
+              const int64_t b_i = (MB == 1) ? cbase[0][j] : (mb_i ? cbase[MB - 1][j] : cbase[0][j]);
+              if (cvalid & (1u << (mb_i * 4 + j))) rnext[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + b_i + c0_i));
+            }
+          }
+        } else {
+          const bool v_i = (MB == 1) ? valid_mb[0] : (mb_i ? valid_mb[1] : valid_mb[0]);
+          const int64_t b_i = (MB == 1) ? base_mb[0] : (mb_i ? base_mb[1] : base_mb[0]);
+          if (has_res && v_i) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + b_i + c0_i);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c0_i + 8 * j < ncols) rnext[j] = __ldg(rp + j);
+          }
         }
       };
       if (part < total_it) issue_residual(part);
@@ -756,26 +869,42 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
         const int nvec = min(4, (ncols - c0) >> 3);  // valid 8-channel vectors in this chunk
         float v[32];
         {
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+          const uint32_t b4 = smem_u32(s_bias + c0);   // explicit ld.shared (a generic LD through the pointer is slower)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = b4[j];
+            const uint4 bu = lds_v4(b4 + 16 * j);
+            const float4 b = make_float4(__uint_as_float(bu.x), __uint_as_float(bu.y), __uint_as_float(bu.z), __uint_as_float(bu.w));
             v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
             v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
             v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
           }
         }
-        if (has_res && valid) {
+        if (has_res) {
+          uint4 rrow[4];
+          if constexpr (kCoalesce) {
+            // coalesced pieces -> staging -> this lane's own row
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < nvec) {
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[j]);
+            for (int j = 0; j < 4; ++j) sts_v4(co_off[j], rcur[j]);
+            __syncwarp();
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h2[e]);
-                v[8 * j + 2 * e + 0] += f.x;
-                v[8 * j + 2 * e + 1] += f.y;
+            for (int j = 0; j < 4; ++j) rrow[j] = lds_v4(own_row + ((static_cast<uint32_t>(j) ^ own_x) << 4));
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rrow[j] = rcur[j];
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < nvec) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rrow[j]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h2[e]);
+                  v[8 * j + 2 * e + 0] += f.x;
+                  v[8 * j + 2 * e + 1] += f.y;
+                }
               }
             }
           }
@@ -786,14 +915,30 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
             for (int i = 0; i < 32; ++i) v[i] = act_apply(p.act, v[i], p.act_slope);
           }
         }
-        if (do_stats) {
+        if (reg_stats) {
+          auto accum = [&](float (&rs)[8], float (&rq)[8]) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float a = 0.f, b = 0.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                a += v[4 * g + j];
+                b = fmaf(v[4 * g + j], v[4 * g + j], b);
+              }
+              rs[g] += valid ? a : 0.f;
+              rq[g] += valid ? b : 0.f;
+            }
+          };
+          if ((c0 >> 5) < kParts) accum(rs0, rq0);   // chunk column part           (slot 0)
+          else accum(rs1, rq1);                      // chunk column part + kParts  (slot 1)
+        } else if (do_stats) {
           float* dst = s_stats + ew * (BN / 2) + 2 * (c0 >> p.cpg_log2);
           if (p.cpg_log2 == 2) chunk_group_stats<8>(v, valid, lane, dst);
           else if (p.cpg_log2 == 3) chunk_group_stats<4>(v, valid, lane, dst);
           else chunk_group_stats<2>(v, valid, lane, dst);
         }
-        if (valid) {
-          if (p.out_h != nullptr) {
+        if (!kCoalesce) {
+          if (valid && p.out_h != nullptr && p.xform_debug != 32) {
             uint4* op = reinterpret_cast<uint4*>(p.out_h + base + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -806,6 +951,26 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
               }
             }
           }
+        } else if (p.out_h != nullptr && p.xform_debug != 32) {   // 32: timing experiment without the fp16 stores
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            sts_v4(own_row + ((static_cast<uint32_t>(j) ^ own_x) << 4), u);
+          }
+          __syncwarp();
+          if (c0 + 8 * (lane & 3) < ncols) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int64_t b_j = (MB == 1) ? cbase[0][j] : (mb ? cbase[MB - 1][j] : cbase[0][j]);
+              if (cvalid & (1u << (mb * 4 + j))) *reinterpret_cast<uint4*>(p.out_h + b_j + c0) = lds_v4(co_off[j]);
+            }
+          }
+          __syncwarp();
+        }
+        if (valid) {
           if (p.out_f != nullptr) {
             float4* op = reinterpret_cast<float4*>(p.out_f + base + c0);
 #pragma unroll
@@ -844,24 +1009,9 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
 
-      if (do_stats) {
-        named_bar_sync(1, kEpiThreads);
-        const int groups_in_tile = BN >> p.cpg_log2;
-        if (et < 2 * groups_in_tile) {
-          const int g = ((t.nt * BN) >> p.cpg_log2) + (et >> 1);
-          // fixed-order fold of the epilogue warps' partials, then one fp64 reduction per (group, moment)
-          float tot = 0.f;
-#pragma unroll
-          for (int wi = 0; wi < kEpiWarps; ++wi) {
-            tot += s_stats[wi * (BN / 2) + et];
-            s_stats[wi * (BN / 2) + et] = 0.f;
-          }
-          atomicAdd(&p.stats[(static_cast<int64_t>(t.frame) * p.groups_total + g) * 2 + (et & 1)],
-                    static_cast<double>(tot));
-        }
-        named_bar_sync(1, kEpiThreads);
-      }
+      if (do_stats && !reg_stats) fold_stats(t.frame, t.nt);
     }
+    if (reg_stats && stats_frame >= 0) flush_reg_stats(stats_frame);
   };
 
   if constexpr (kRegSplit) {
@@ -872,10 +1022,10 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       else if (warp == kWarpMma) role_mma();
       else if (warp == kWarpTmaB) role_tma_b();
     } else if (warp < kXformWarp0 + kXformWarps) {
-      setmaxnreg_dec<72>();
+      setmaxnreg_dec<64>();
       role_xform();
     } else {
-      setmaxnreg_inc<136>();
+      setmaxnreg_inc<144>();
       role_epi();
     }
   } else {
@@ -932,7 +1082,7 @@ constexpr size_t conv_smem_bytes() {
   constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + (Cfg::kMB == 1 ? 6 : 5) * b_bytes
                                : Cfg::kStages * (Cfg::kMB * kABytes + b_bytes);
   return 1024 /*align slack*/ + ring + (3 * Cfg::kStages + 2 * kHaloBStagesMax + 4) * 8 + 16 +
-         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + 64;
+         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + (BN == 128 ? kEpiWarps * 2048 : 0) + 64;
 }
 
 template <int BN, bool PAIR, bool HALO, bool EPI = false>
