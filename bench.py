@@ -195,8 +195,10 @@ def run_b200_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not os.environ.get("WFK_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would precede the JSON line
+    # NCCL prints its version banner (and anything NCCL_DEBUG asks for) on stdout: point fd 1 at stderr while the job
+    # runs so that the ONE JSON line is the only thing rank 0 writes to the real stdout
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
@@ -326,7 +328,8 @@ def run_b200_arm(args):
                                     "sample": CPU_SAMPLE_DESC, "sample_seconds": r["measured_s"]}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -50,6 +50,15 @@ int64_t wfk_launch_count(void);
 int wfk_stage_vil_u8(const uint8_t* nhwt, int n, int h, int w, int t, void* out_ntchw, int out_dtype,
                      void* stream);
 
+/* 8(f).2  Event windowing + staging in one pass.  Replaces the sequence slicing of SEVIRDataLoader._idx_sample /
+ *     _sequent_sample (pipeline/datasets/sevir/sevir.py:851-889: event_batch[e, :, :, s*stride : s*stride+seq_len])
+ *     followed by preprocess_data_dict + change_layout.  events: [num_events, h, w, t_raw] uint8 resident on the device
+ *     (SEVIR VIL events: t_raw = 49); windows: DEVICE int32 [n][2] = (event index, first raw frame); output
+ *     [n, t, 1, h, w] as wfk_stage_vil_u8.  Window bounds (event < num_events, t0 + t <= t_raw) are the caller's
+ *     contract (checked by the Python wrapper). */
+int wfk_stage_vil_windows(const uint8_t* events, int num_events, int h, int w, int t_raw, const int32_t* windows, int n,
+                          int t, void* out_ntchw, int out_dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a8  Latent predictor.  Replaces the residual framing + nn.Linear(13*C, 12*C) + permutes of
  *     Model.validation_step (experiments/v1_experiments/pretrained_ae_linear_sevir/train.py:
@@ -310,6 +319,12 @@ int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const float* gamm
  * Replaces torch.softmax(attention_scores.float(), dim=-1) (attention.py:171); `scale` is the
  * baddbmm alpha (attention.py:148, 168). */
 int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, void* stream);
+
+/* a7  DiagonalGaussianDistribution arithmetic (pipeline/models/autoencoderkl/distributions.py:26-42) in one pass:
+ * moments [n, 2*lc, hw] fp32 -> logvar = clamp(moments[:, lc:], -30, 20), std = exp(0.5*logvar), var = exp(logvar)
+ * (each [n, lc, hw], any may be NULL) and, when noise != NULL, sample = mean + std * noise. */
+int wfk_gaussian_posterior(const float* moments, int n, int lc, int hw, float* logvar, float* std, float* var,
+                           const float* noise, float* sample, void* stream);
 
 /* [n, hw, c] fp32 -> [n, c, hw] fp32: the conv-GEMM's NHWC result to the model-facing NCHW moments tensor
  * (AutoencoderKL.encode returns [B, 2*latent_channels, h, w], autoencoder_kl.py:80-84). */

@@ -183,6 +183,16 @@ def test_drop_in_interface(model, akl_weights):
     g = torch.Generator(device=DEV).manual_seed(1)
     assert torch.equal(s1, post.sample(generator=g))
     assert post.kl().shape == (2,) and post.nll(s1).shape == (2,)
+    # posterior arithmetic (wfk_gaussian_posterior) vs the reference formulas (distributions.py:26-42)
+    lv = post.parameters[:, 4:].clamp(-30.0, 20.0)
+    assert torch.equal(post.logvar, lv) and torch.equal(post.mean, post.parameters[:, :4])
+    torch.testing.assert_close(post.std, torch.exp(0.5 * lv), rtol=2e-6, atol=0)
+    torch.testing.assert_close(post.var, torch.exp(lv), rtol=2e-6, atol=0)
+    nz = torch.randn_like(lv)
+    torch.testing.assert_close(post.sample_with_noise(nz), post.mean + post.std * nz, rtol=1e-6, atol=1e-7)
+    from weatherforecastingtoolkit_b200.models.autoencoderkl import DiagonalGaussianDistribution
+    det = DiagonalGaussianDistribution(post.parameters, deterministic=True)
+    assert float(det.std.abs().max()) == 0.0 and torch.equal(det.sample(), det.mean)
     dec, post2 = model(x, sample_posterior=False, return_posterior=True)
     assert dec.shape == (2, 1, 64, 64)
     model.enable_slicing()

@@ -230,3 +230,40 @@ def test_stem_tc_vs_conv2d(lib, n, cin, h, w, cout, ones, cpg):
         z = F.conv2d(x, pw.reshape(cin, cin, 1, 1), pb)
         want32 = F.conv2d(z, wt, bias, padding=1).permute(0, 2, 3, 1)
         assert rel_l2(out.float(), want32) < 5e-3
+
+
+# ------------------------------------------------------------------ event windowing + staging
+def test_stage_vil_windows_bitexact(lib):
+    """Windows cut from resident uint8 events == the reference's slicing (sevir.py:879-889) + staging formula."""
+    from oracle import akl_oracle as O
+    from weatherforecastingtoolkit_b200.rollout import sequent_windows, stage_vil, stage_vil_windows
+    g = torch.Generator().manual_seed(9)
+    events = torch.randint(0, 256, (3, 48, 40, 49), generator=g, dtype=torch.uint8)
+    wins = sequent_windows(3, raw_seq_len=49, seq_len=25, stride=12)
+    assert wins == [(0, 0), (0, 12), (0, 24), (1, 0), (1, 12), (1, 24), (2, 0), (2, 12), (2, 24)]
+    got = stage_vil_windows(events.to(DEV), wins, seq_len=25)
+    ref_batch = torch.stack([events[e, :, :, t0:t0 + 25] for e, t0 in wins])          # the reference's sampled_seq
+    want = O.stage_vil(ref_batch).permute(0, 3, 1, 2).unsqueeze(2).contiguous()
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(got, stage_vil(ref_batch.to(DEV)))                               # == slice-then-stage
+    with pytest.raises(ValueError):
+        stage_vil_windows(events.to(DEV), [(0, 30)], seq_len=25)
+    with pytest.raises(ValueError):
+        stage_vil_windows(events.to(DEV), [(3, 0)], seq_len=25)
+
+
+# ------------------------------------------------------------------ epoch accumulator (SURVEY 8f.3)
+def test_metric_accumulator_equals_concatenated_batch(lib):
+    from weatherforecastingtoolkit_b200 import metrics as M
+    p, t = metric_case_inputs("rand_2x10x64")
+    acc = M.MetricAccumulator()
+    acc.update(p[:1].to(DEV), t[:1].to(DEV))
+    acc.update(p[1:].to(DEV), t[1:].to(DEV))
+    whole = M.metric_partials(p.to(DEV), t.to(DEV))
+    got = acc.partials()
+    assert np.array_equal(got.ints, whole.ints)                       # exact integer counts, additive over batches
+    assert np.allclose(got.floats[:6], whole.floats[:6], rtol=1e-9, atol=0), (got.floats, whole.floats)  # [6:] reserved
+    a, b = acc.compute(extended=True), M.calc_metrics(p.to(DEV), t.to(DEV), extended=True)
+    for k in b:
+        both_nan = a[k] != a[k] and b[k] != b[k]
+        assert both_nan or a[k] == b[k] or abs(a[k] - b[k]) <= 1e-7 * max(1.0, abs(b[k])), (k, a[k], b[k])

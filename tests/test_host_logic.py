@@ -122,11 +122,8 @@ def test_drop_in_module_surface_cpu():
         m.encode(torch.zeros(1, 1, 64, 64))          # CPU tensor: refuses, no fallback
     with pytest.raises(ValueError):
         AutoencoderKL(down_block_types=("Foo",), up_block_types=("UpDecoderBlock2D",))
-    d = DiagonalGaussianDistribution(torch.randn(2, 8, 4, 4))
-    assert torch.equal(d.mode(), d.mean) and d.sample().shape == (2, 4, 4, 4)
-    assert d.kl().shape == (2,)
-    det = DiagonalGaussianDistribution(torch.randn(2, 8, 4, 4), deterministic=True)
-    assert float(det.std.abs().max()) == 0.0
+    with pytest.raises(RuntimeError):                 # the posterior arithmetic is a CUDA kernel too: no CPU path
+        DiagonalGaussianDistribution(torch.randn(2, 8, 4, 4))
 
 
 def test_rollout_wrappers_refuse_cpu():
@@ -138,3 +135,30 @@ def test_rollout_wrappers_refuse_cpu():
     assert p(torch.zeros(3, 52)).shape == (3, 48)       # nn.Linear forward kept for training code
     with pytest.raises(RuntimeError):
         p.rollout(torch.zeros(1, 25, 4, 8, 8))
+
+
+def test_sequent_windows_matches_reference_sampler():
+    """(event, first frame) order of SEVIRDataLoader._idx_sample (pipeline/datasets/sevir/sevir.py:864-877),
+    restated: num_seq_per_event = 1 + (raw_seq_len - seq_len) // stride (:327-328)."""
+    from weatherforecastingtoolkit_b200.rollout import sequent_windows
+    raw, seq, stride, bs = 49, 25, 12, 4
+    per_event = 1 + (raw - seq) // stride
+    for index in range(3):
+        event_idx, seq_idx = (index * bs) // per_event, (index * bs) % per_event
+        want = []
+        while len(want) < bs:
+            want.append((event_idx, seq_idx * stride))
+            seq_idx += 1
+            if seq_idx >= per_event:
+                event_idx, seq_idx = event_idx + 1, 0
+        assert sequent_windows(10, raw, seq, stride, start=index * bs, count=bs) == want
+    assert len(sequent_windows(2, 49, 25, 12)) == 6 and sequent_windows(1, 25, 25, 12) == [(0, 0)]
+
+
+def test_metric_accumulator_refuses_cpu_and_empty():
+    from weatherforecastingtoolkit_b200 import metrics as M
+    acc = M.MetricAccumulator()
+    with pytest.raises(RuntimeError):
+        acc.compute()
+    with pytest.raises(RuntimeError):
+        acc.update(torch.rand(1, 2, 1, 32, 32), torch.rand(1, 2, 1, 32, 32))

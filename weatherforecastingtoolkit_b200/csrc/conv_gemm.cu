@@ -738,6 +738,16 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       s_stats[ew * (BN / 2) + 2 * (8 * (part + kParts * slot) + g) + m] = vals[0];
       fold_stats(frame, 0);
     };
+    // swizzled staging offsets: this lane's OWN row (unit j) and the coalesced (row 8j + lane/4, unit lane & 3) slots
+    const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(ew) * 2048u;
+    const uint32_t own_row = stg + static_cast<uint32_t>(lane) * 64u;
+    const uint32_t own_x = static_cast<uint32_t>((lane >> 1) & 3);
+    uint32_t co_off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t rr = 8u * j + (lane >> 2);
+      co_off[j] = stg + rr * 64u + ((static_cast<uint32_t>(lane & 3) ^ ((rr >> 1) & 3u)) << 4);
+    }
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord t = decode_tile(p, tile);
       const int row = quarter * 32 + lane;
@@ -783,35 +793,42 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       // K = 9*128 layers LSU-bound (measured: +23 % with the stores removed, +30 % on residual layers).
       int64_t cbase[MB][4];
       uint32_t cvalid = 0;
+      if constexpr (kCoalesce) {
 #pragma unroll
-      for (int mb = 0; mb < MB; ++mb) {
-        const int blk = static_cast<int>(cta_rank) * MB + mb;
-        const int bx = p.stack_x ? t.tx * kBlocksPerTile + blk : t.tx;
-        const int by = p.stack_x ? t.ty : t.ty * kBlocksPerTile + blk;
+        for (int mb = 0; mb < MB; ++mb) {
+          const int blk = static_cast<int>(cta_rank) * MB + mb;
+          const int bx = p.stack_x ? t.tx * kBlocksPerTile + blk : t.tx;
+          const int by = p.stack_x ? t.ty : t.ty * kBlocksPerTile + blk;
+          if (p.bw_log2 == 3) {
+            // 8-pixel-wide blocks (every HALO tile): access j is simply j image rows below access 0
+            const int rr = quarter * 32 + (lane >> 2);
+            const int py = by * bh + (rr >> 3);
+            const int px = bx * 8 + (rr & 7);
+            const int oy = py * p.out_sy + (t.phase >> 1);
+            const int ox = px * p.out_sx + (t.phase & 1);
+            const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
+            const int64_t b0 = pix * p.ldc + static_cast<int64_t>(t.nt) * BN + 8 * (lane & 3);
+            const int64_t row_step = static_cast<int64_t>(p.out_sy) * p.out_cols * p.ldc;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int rr = quarter * 32 + 8 * j + (lane >> 2);
-          const int py = by * bh + (rr >> p.bw_log2);
-          const int px = bx * bw + (rr & (bw - 1));
-          if (py < p.tile_h && px < p.tile_w) cvalid |= 1u << (mb * 4 + j);
-          const int oy = py * p.out_sy + (t.phase >> 1);
-          const int ox = px * p.out_sx + (t.phase & 1);
-          const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
-          cbase[mb][j] = pix * p.ldc + static_cast<int64_t>(t.nt) * BN + 8 * (lane & 3);
+            for (int j = 0; j < 4; ++j) {
+              cbase[mb][j] = b0 + j * row_step;
+              if (py + j < p.tile_h && px < p.tile_w) cvalid |= 1u << (mb * 4 + j);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = quarter * 32 + 8 * j + (lane >> 2);
+              const int py = by * bh + (rr >> p.bw_log2);
+              const int px = bx * bw + (rr & (bw - 1));
+              if (py < p.tile_h && px < p.tile_w) cvalid |= 1u << (mb * 4 + j);
+              const int oy = py * p.out_sy + (t.phase >> 1);
+              const int ox = px * p.out_sx + (t.phase & 1);
+              const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
+              cbase[mb][j] = pix * p.ldc + static_cast<int64_t>(t.nt) * BN + 8 * (lane & 3);
+            }
+          }
         }
       }
-      const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(ew) * 2048u;
-      // swizzled staging offsets: this lane's OWN row (unit j) and the coalesced (row 8j + lane/4, unit lane & 3) slots
-      const uint32_t own_row = stg + static_cast<uint32_t>(lane) * 64u;
-      const uint32_t own_x = static_cast<uint32_t>((lane >> 1) & 3);
-      uint32_t co_off[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t rr = 8u * j + (lane >> 2);
-        co_off[j] = stg + rr * 64u + ((static_cast<uint32_t>(lane & 3) ^ ((rr >> 1) & 3u)) << 4);
-      }
-      // residual values are prefetched one chunk ahead (and before the accumulator is even ready) so
-      // their global-memory latency is off the epilogue's critical path
       uint4 rnext[4];
       auto issue_residual = [&](int it) {
         const int mb_i = (MB == 1) ? 0 : (it >= nchunks ? 1 : 0);

@@ -202,6 +202,28 @@ __global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int64_t to
   out[i] = in[(n * hw + p) * c + ch];
 }
 
+// DiagonalGaussianDistribution arithmetic in one pass over the moments tensor [n, 2*lc, hw]:
+// logvar = clamp(moments[:, lc:], -30, 20); std = exp(0.5*logvar); var = exp(logvar); optionally
+// sample = mean + std * noise (reference pipeline/models/autoencoderkl/distributions.py:26-42).
+__global__ void __launch_bounds__(256) gaussian_posterior_kernel(const float* __restrict__ moments, int lc, int hw,
+                                                                 int64_t total, float* __restrict__ logvar,
+                                                                 float* __restrict__ stdv, float* __restrict__ var,
+                                                                 const float* __restrict__ noise,
+                                                                 float* __restrict__ sample) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // index into [n, lc, hw]
+  if (i >= total) return;
+  const int64_t per = static_cast<int64_t>(lc) * hw;
+  const int64_t n = i / per, r = i - n * per;
+  const float mean = moments[n * 2 * per + r];
+  float lv = moments[n * 2 * per + per + r];
+  lv = fminf(fmaxf(lv, -30.f), 20.f);
+  const float sd = expf(0.5f * lv);
+  if (logvar != nullptr) logvar[i] = lv;
+  if (stdv != nullptr) stdv[i] = sd;
+  if (var != nullptr) var[i] = expf(lv);
+  if (sample != nullptr) sample[i] = mean + sd * noise[i];
+}
+
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, int64_t n, __half* __restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2half_rn(in[i]);
@@ -247,6 +269,17 @@ extern "C" int wfk_softmax_rows(const float* scores, int64_t rows, int cols, flo
   wfk::softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, cols * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       scores, cols, scale, static_cast<__half*>(probs));
   return wfk::launched("softmax_rows_kernel");
+}
+
+extern "C" int wfk_gaussian_posterior(const float* moments, int n, int lc, int hw, float* logvar, float* std, float* var,
+                                      const float* noise, float* sample, void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(moments && n > 0 && lc > 0 && hw > 0, "bad argument");
+  WFK_REQUIRE((sample == nullptr) == (noise == nullptr), "noise and sample must both be given or both NULL");
+  const int64_t total = static_cast<int64_t>(n) * lc * hw;
+  wfk::gaussian_posterior_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      moments, lc, hw, total, logvar, std, var, noise, sample);
+  return wfk::launched("gaussian_posterior_kernel");
 }
 
 extern "C" int wfk_nhwc_to_nchw_f32(const float* in, int n, int hw, int c, float* out, void* stream) {

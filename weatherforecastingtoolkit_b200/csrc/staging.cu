@@ -12,15 +12,20 @@ namespace wfk {
 
 constexpr int kStagePix = 512;  // pixels per block
 
+// `windows` (optional): per output sequence (event index, first raw frame) into an event tensor [E, hw, t_src]
+// (SEVIR events hold t_src = 49 frames; a sequence is the slice [t0, t0 + t), sevir.py:851-889). Without it the
+// input is the already-sliced batch [n, hw, t] (t_src == t, t0 == 0).
 template <bool HALF_OUT>
-__global__ void __launch_bounds__(256) stage_vil_kernel(const uint8_t* __restrict__ in, int hw, int t,
-                                                        void* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t s_bytes[];  // [kStagePix * t]
+__global__ void __launch_bounds__(256) stage_vil_kernel(const uint8_t* __restrict__ in, int hw, int t, int t_src,
+                                                        const int32_t* __restrict__ windows, void* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t s_bytes[];  // [kStagePix * t_src]
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * kStagePix;
   const int npix = min(kStagePix, hw - p0);
-  const int nbytes = npix * t;
-  const uint8_t* src = in + (static_cast<int64_t>(n) * hw + p0) * t;
+  const int nbytes = npix * t_src;
+  const int ev = windows ? windows[2 * n] : n;
+  const int t0 = windows ? windows[2 * n + 1] : 0;
+  const uint8_t* src = in + (static_cast<int64_t>(ev) * hw + p0) * t_src;
   if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const int nvec = nbytes >> 4;
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -40,7 +45,7 @@ __global__ void __launch_bounds__(256) stage_vil_kernel(const uint8_t* __restric
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = pg + j;
-      v[j] = (p < npix) ? __fmul_rn(static_cast<float>(s_bytes[p * t + ti]), scale) : 0.f;
+      v[j] = (p < npix) ? __fmul_rn(static_cast<float>(s_bytes[p * t_src + t0 + ti]), scale) : 0.f;
     }
     const int64_t o = (static_cast<int64_t>(n) * t + ti) * hw + p0 + pg;
     if (pg + 3 < npix && ((o & 3) == 0)) {
@@ -74,7 +79,23 @@ extern "C" int wfk_stage_vil_u8(const uint8_t* nhwt, int n, int h, int w, int t,
   dim3 grid((hw + wfk::kStagePix - 1) / wfk::kStagePix, n);
   const size_t smem = static_cast<size_t>(wfk::kStagePix) * t;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (out_dtype == 1) wfk::stage_vil_kernel<true><<<grid, 256, smem, s>>>(nhwt, hw, t, out_ntchw);
-  else wfk::stage_vil_kernel<false><<<grid, 256, smem, s>>>(nhwt, hw, t, out_ntchw);
+  if (out_dtype == 1) wfk::stage_vil_kernel<true><<<grid, 256, smem, s>>>(nhwt, hw, t, t, nullptr, out_ntchw);
+  else wfk::stage_vil_kernel<false><<<grid, 256, smem, s>>>(nhwt, hw, t, t, nullptr, out_ntchw);
   return wfk::launched("stage_vil_kernel");
+}
+
+extern "C" int wfk_stage_vil_windows(const uint8_t* events, int num_events, int h, int w, int t_raw, const int32_t* windows,
+                                     int n, int t, void* out_ntchw, int out_dtype, void* stream) {
+  WFK_REQUIRE_INIT();
+  WFK_REQUIRE(events && windows && out_ntchw, "null pointer");
+  WFK_REQUIRE(num_events > 0 && n > 0 && n <= 65535 && h > 0 && w > 0, "unsupported shape");
+  WFK_REQUIRE(t > 0 && t <= t_raw && t_raw <= 64, "need 0 < t (%d) <= t_raw (%d) <= 64", t, t_raw);
+  WFK_REQUIRE(out_dtype == 0 || out_dtype == 1, "out_dtype must be 0 (f32) or 1 (f16)");
+  const int hw = h * w;
+  dim3 grid((hw + wfk::kStagePix - 1) / wfk::kStagePix, n);
+  const size_t smem = static_cast<size_t>(wfk::kStagePix) * t_raw;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_dtype == 1) wfk::stage_vil_kernel<true><<<grid, 256, smem, s>>>(events, hw, t, t_raw, windows, out_ntchw);
+  else wfk::stage_vil_kernel<false><<<grid, 256, smem, s>>>(events, hw, t, t_raw, windows, out_ntchw);
+  return wfk::launched("stage_vil_kernel(windows)");
 }

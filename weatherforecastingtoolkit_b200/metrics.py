@@ -158,6 +158,37 @@ def metric_partials(pred, target, thresholds: Sequence[float] = THRESHOLDS, clam
     return _to_host(dev_struct, len(thresholds))
 
 
+class MetricAccumulator:
+    """Epoch-level running scores: the device-resident partials of every ``update`` are added on the
+    GPU without a host sync; ``compute`` does one all-reduce (optional) and one D2H copy and returns the scores of
+    everything seen since the last ``reset`` -- a ratio of sums over the epoch, where the reference's
+    ``log_dict(on_epoch=True)`` (pipeline/helpers.py:151-153) averages per-batch ratios."""
+
+    def __init__(self, thresholds: Sequence[float] = THRESHOLDS):
+        self.thresholds = list(thresholds)
+        self._acc: Optional[torch.Tensor] = None
+        self.batches = 0
+
+    def reset(self) -> None:
+        self._acc, self.batches = None, 0
+
+    def update(self, pred: torch.Tensor, target: torch.Tensor) -> None:
+        part = metric_partials_device(pred, target, self.thresholds, clamp=True)
+        self._acc = part if self._acc is None else _add_device(self._acc, part)
+        self.batches += 1
+
+    def partials(self, process_group=None) -> MetricPartials:
+        if self._acc is None:
+            raise RuntimeError("MetricAccumulator.compute() before any update()")
+        dev_struct = self._acc
+        if process_group is not None:
+            dev_struct = all_reduce_partials(dev_struct, None if process_group is True else process_group)
+        return _to_host(dev_struct, len(self.thresholds))
+
+    def compute(self, extended: bool = False, process_group=None) -> Dict[str, float]:
+        return scores_from_partials(self.partials(process_group), extended=extended)
+
+
 # ------------------------------------------------------------------ scores from counts / sums
 def _f32(x) -> np.float32:
     return np.float32(x)

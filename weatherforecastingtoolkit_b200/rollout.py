@@ -45,6 +45,43 @@ def stage_vil(batch_u8_nhwt: torch.Tensor, dtype: torch.dtype = torch.float32) -
     return out
 
 
+def sequent_windows(num_events: int, raw_seq_len: int = 49, seq_len: int = 25, stride: int = 12, start: int = 0,
+                    count: Optional[int] = None):
+    """(event, first frame) pairs in the order of the reference's sequential sampler
+    (``SEVIRDataLoader._idx_sample``, pipeline/datasets/sevir/sevir.py:864-877): ``num_seq_per_event =
+    1 + (raw_seq_len - seq_len) // stride`` (:327-328) windows per event, events in order; ``start`` / ``count``
+    select a batch (index * batch_size, batch_size)."""
+    per_event = 1 + (raw_seq_len - seq_len) // stride
+    total = per_event * num_events
+    stop = total if count is None else min(total, start + count)
+    return [(i // per_event, (i % per_event) * stride) for i in range(start, stop)]
+
+
+def stage_vil_windows(events_u8: torch.Tensor, windows, seq_len: int = 25, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """uint8 SEVIR events [E, H, W, T_raw] resident on the GPU + (event, t0) windows -> normalised [N, seq_len, 1, H, W]:
+    the slicing of ``_idx_sample`` (sevir.py:879-889) fused with ``preprocess_data_dict`` + ``change_layout`` (no
+    intermediate uint8 batch, no 4x fp32 host-to-device inflation)."""
+    if events_u8.dtype != torch.uint8 or events_u8.ndim != 4:
+        raise TypeError("expected a uint8 [E, H, W, T_raw] tensor")
+    lib = _lib_for(events_u8)
+    ev = events_u8.contiguous()
+    e, h, w, t_raw = ev.shape
+    win = torch.as_tensor(windows, dtype=torch.int32).reshape(-1, 2)
+    if win.numel() == 0:
+        raise ValueError("no windows")
+    if int(win[:, 0].min()) < 0 or int(win[:, 0].max()) >= e or int(win[:, 1].min()) < 0 or int(win[:, 1].max()) + seq_len > t_raw:
+        raise ValueError("window out of range")
+    if dtype not in (torch.float32, torch.float16):
+        raise ValueError("dtype must be float32 or float16")
+    n = win.shape[0]
+    win_d = win.to(ev.device)
+    out = torch.empty((n, seq_len, 1, h, w), dtype=dtype, device=ev.device)
+    stream = torch.cuda.current_stream(ev.device).cuda_stream
+    _cabi.check(lib.wfk_stage_vil_windows(ev.data_ptr(), e, h, w, t_raw, win_d.data_ptr(), n, seq_len, out.data_ptr(),
+                                          0 if dtype == torch.float32 else 1, stream), "wfk_stage_vil_windows")
+    return out
+
+
 class LatentLinearPredictor(nn.Linear):
     """``self.predictor = nn.Linear(input_frames * 4, pred_frames * 4)`` (train.py:67). ``forward`` is
     inherited (training stays PyTorch, out of scope); ``rollout`` is the fused inference kernel."""
@@ -103,7 +140,7 @@ class Autoencoder(nn.Module):
             post = self.autoencoder.encode(flat[i:i + self.frames_per_call])
             if noise is not None:
                 nz = noise.reshape(b * t, *noise.shape[2:])[i:i + self.frames_per_call]
-                outs.append(post.mean + post.std * nz)
+                outs.append(post.sample_with_noise(nz))
             elif self.posterior == "sample":
                 outs.append(post.sample())
             else:
