@@ -92,6 +92,16 @@ int wfk_dlinear(const float* x, int64_t x_batch_stride, const float* w_seasonal,
                 int group, int kernel_size, int individual, int framed, float* pred, float* tgt,
                 double* loss_sums, void* stream);
 
+/* 8(f).4  ConvModel latent compressor, one launch for the whole network.  Replaces ConvEncoder / ConvDecoder / ConvModel
+ *     .forward (experiments/v1_experiments/pretrained_ae_convae_sevir/train.py:58-143) and the HuberLoss of its
+ *     validation_step (train.py:160, 193-194).  x [n, cin, 48, 48] fp32 latent frames; weights: HOST array of 34 DEVICE
+ *     fp32 pointers in module order: conv0 (w, b); LayerNorm (w, b) of conv0, down1..3, up1..3; down1..3 (w, b);
+ *     to_latent (w, b); to_reconstruction (w, b); up1..3 (w, b); conv_out (w, b).  Writes z [n, latent_dim],
+ *     recon [n, cin, 48, 48] and, when non-NULL, huber_sums[2] (double: sum of Huber(recon, x), element count;
+ *     caller-zeroed). */
+int wfk_convmodel_forward(const float* x, int n, int cin, int latent_dim, const float* const* weights, float* z,
+                          float* recon, double* huber_sums, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a10-a14  Fused skill-score pass.  Replaces the 41 passes of calc_metrics
  *     (pipeline/metrics.py:86-133): clamp(0,1) (:92-93); _hit_miss_fa_cn counts (:9-16) at the

@@ -55,3 +55,24 @@ def dlinear_rollout(v, w_seasonal, b_seasonal, w_trend, b_trend, kernel_size: in
     pred = dlinear_forward(x, w_seasonal, b_seasonal, w_trend, b_trend, kernel_size).reshape(b, t - in_frames, c, h, w)
     loss = F.mse_loss(pred, tgt)
     return pred + inp_t, tgt + inp_t, loss
+
+
+def convmodel_forward(x, sd):
+    """``ConvModel.forward`` (experiments/v1_experiments/pretrained_ae_convae_sevir/train.py:133-143) with
+    ``ConvEncoder`` (:58-89) and ``ConvDecoder`` (:92-117) restated on a state_dict. x [B, T, 4, 48, 48] -> (z, recon)."""
+    b, t, c, h, w = x.shape
+    y = x.reshape(b * t, c, h, w)
+
+    def ln_act(v, p):
+        return F.leaky_relu(F.layer_norm(v, tuple(v.shape[1:]), sd[p + ".weight"], sd[p + ".bias"], 1e-5))
+    y = ln_act(F.conv2d(y, sd["encoder.conv0.0.weight"], sd["encoder.conv0.0.bias"], padding=1), "encoder.conv0.1")
+    for name in ("down1", "down2", "down3"):
+        y = ln_act(F.conv2d(y, sd[f"encoder.{name}.0.weight"], sd[f"encoder.{name}.0.bias"], stride=2, padding=1),
+                   f"encoder.{name}.1")
+    z = F.linear(y.reshape(b * t, -1), sd["to_latent.weight"], sd["to_latent.bias"])
+    y = F.linear(z, sd["to_reconstruction.weight"], sd["to_reconstruction.bias"]).reshape(b * t, 8, 6, 6)
+    for name in ("up1", "up2", "up3"):
+        y = ln_act(F.conv_transpose2d(y, sd[f"decoder.{name}.0.weight"], sd[f"decoder.{name}.0.bias"], stride=2, padding=1),
+                   f"decoder.{name}.1")
+    y = F.conv2d(y, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
+    return z, y.reshape(b, t, c, h, w)

@@ -177,6 +177,45 @@ def gen_vit(out):
     out["vit_tokens"] = z.numpy()
 
 
+CONVMODEL_SCRIPT = "experiments/v1_experiments/pretrained_ae_convae_sevir/train.py"
+
+
+def convmodel_case(seed=0, b=2, t=3):
+    """(state_dict, latents [b, t, 4, 48, 48]): kaiming-normal weights like ConvModel.init_weights (train.py:127-131),
+    random (non-trivial) LayerNorm affine parameters and biases."""
+    from weatherforecastingtoolkit_b200.predictors import ConvModel as Mine
+    torch.manual_seed(1234 + seed)
+    m = Mine()
+    sd = {}
+    for k, v in m.state_dict().items():
+        g = torch.Generator().manual_seed(S._name_seed("convmodel." + k, seed))
+        leaf = k.rsplit(".", 1)[-1]
+        is_ln = v.ndim == 3
+        if leaf == "weight" and not is_ln:
+            fan_in = int(np.prod(v.shape[1:]))
+            sd[k] = torch.randn(v.shape, generator=g) * float(np.sqrt(2.0 / (1 + 0.01 ** 2) / fan_in))
+        elif leaf == "weight":
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+    g = torch.Generator().manual_seed(S._name_seed("convmodel.x", seed))
+    x = torch.randn((b, t, 4, 48, 48), generator=g)
+    return sd, x
+
+
+def gen_convmodel(out):
+    ns = ref_script_classes(CONVMODEL_SCRIPT, ["ConvEncoder", "ConvDecoder", "ConvModel"])
+    sd, x = convmodel_case()
+    m = ns["ConvModel"](latent_dim=512).eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        z, rec = m(x)
+        loss = torch.nn.HuberLoss()(rec, x)
+    out["convmodel_z"] = z.numpy()
+    out["convmodel_recon"] = rec.numpy()
+    out["convmodel_huber"] = np.array(loss.item())
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     out = {}
@@ -187,7 +226,7 @@ def main():
     print("wrote extra_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
-EXTRA_GENERATORS = [gen_discriminator, gen_posaware, gen_vit]
+EXTRA_GENERATORS = [gen_discriminator, gen_posaware, gen_vit, gen_convmodel]
 
 if __name__ == "__main__":
     main()

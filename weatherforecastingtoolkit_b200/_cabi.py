@@ -78,6 +78,8 @@ _PROTOTYPES = {
     "wfk_dlinear": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
+    "wfk_convmodel_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "wfk_metrics_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "wfk_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
                               C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

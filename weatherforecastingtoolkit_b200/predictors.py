@@ -147,3 +147,96 @@ def dlinear_config(seq_len=13, pred_len=12, individual=False, enc_in=9216, kerne
     """The ``dlinear:`` block of the reference configs (e.g. pretrained_ae_dlinear_sevir/config.yaml:4-9)."""
     return SimpleNamespace(seq_len=seq_len, pred_len=pred_len, individual=individual, enc_in=enc_in,
                            kernel_size=kernel_size)
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvModel latent compressor (experiments/v1_experiments/pretrained_ae_convae_sevir/train.py:58-143)
+class ConvEncoder(nn.Module):
+    """Parameter container of train.py:58-89."""
+
+    def __init__(self, in_channels=4, bottleneck_channels=8):
+        super().__init__()
+        bc = bottleneck_channels
+
+        def down(hw):
+            return nn.Sequential(nn.Conv2d(bc, bc, kernel_size=4, stride=2, padding=1), nn.LayerNorm([bc, hw, hw]), nn.LeakyReLU())
+        self.conv0 = nn.Sequential(nn.Conv2d(in_channels, bc, kernel_size=3, padding=1), nn.LayerNorm([bc, 48, 48]), nn.LeakyReLU())
+        self.down1, self.down2, self.down3 = down(24), down(12), down(6)
+
+
+class ConvDecoder(nn.Module):
+    """Parameter container of train.py:92-117."""
+
+    def __init__(self, bottleneck_channels=8, out_channels=4):
+        super().__init__()
+        bc = bottleneck_channels
+
+        def up(hw):
+            return nn.Sequential(nn.ConvTranspose2d(bc, bc, kernel_size=4, stride=2, padding=1), nn.LayerNorm([bc, hw, hw]), nn.LeakyReLU())
+        self.up1, self.up2, self.up3 = up(12), up(24), up(48)
+        self.conv_out = nn.Conv2d(bc, out_channels, kernel_size=3, padding=1)
+
+
+class ConvModel(nn.Module):
+    """``ConvModel(latent_dim=512)`` (train.py:119-143): same module tree / ``state_dict`` keys / init; ``forward`` runs the
+    whole network as ONE kernel (``wfk_convmodel_forward``), one CTA per latent frame."""
+
+    def __init__(self, latent_dim=512):
+        super().__init__()
+        self.encoder = ConvEncoder()
+        self.decoder = ConvDecoder()
+        self.to_latent = nn.Linear(8 * 6 * 6, latent_dim)
+        self.to_reconstruction = nn.Linear(latent_dim, 8 * 6 * 6)
+        self.latent_dim = latent_dim
+        self.apply(self.init_weights)
+        self._packed = None
+
+    def init_weights(self, m):
+        if isinstance(m, (nn.Linear, nn.Conv2d, nn.ConvTranspose2d)):
+            nn.init.kaiming_normal_(m.weight, nonlinearity='leaky_relu')
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+
+    def _modules_in_kernel_order(self):
+        e, d = self.encoder, self.decoder
+        lns = [e.conv0[1], e.down1[1], e.down2[1], e.down3[1], d.up1[1], d.up2[1], d.up3[1]]
+        return ([e.conv0[0]] + lns + [e.down1[0], e.down2[0], e.down3[0], self.to_latent, self.to_reconstruction,
+                                      d.up1[0], d.up2[0], d.up3[0], d.conv_out])
+
+    def _pack(self, device):
+        mods = self._modules_in_kernel_order()
+        key = (str(device), sum(p._version for p in self.parameters()))
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[1]
+        import ctypes as C
+        tensors = []
+        for m in mods:
+            tensors += [m.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
+                        m.bias.detach().to(device=device, dtype=torch.float32).contiguous()]
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        self._packed = (key, (tensors, arr))
+        return self._packed[1]
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, return_loss: bool = False):
+        """x [B, T, 4, 48, 48] fp32 CUDA latents -> (z [B*T, latent_dim], recon [B, T, 4, 48, 48]) (train.py:133-143);
+        with ``return_loss`` also ``nn.HuberLoss()(recon, x)`` as computed by validation_step (train.py:193-194)."""
+        if not x.is_cuda:
+            raise RuntimeError("this path runs on a B200 only (no CPU fallback): pass CUDA tensors")
+        if x.ndim != 5 or tuple(x.shape[3:]) != (48, 48):
+            raise ValueError(f"expected [B, T, C, 48, 48] latents (the LayerNorm shapes are fixed), got {tuple(x.shape)}")
+        b, t, c = x.shape[:3]
+        if c != self.encoder.conv0[0].in_channels:
+            raise ValueError("channel count does not match encoder.conv0")
+        lib = _cabi.init(x.device.index if x.device.index is not None else 0)
+        tensors, arr = self._pack(x.device)
+        xf = x.detach().to(torch.float32).contiguous()
+        z = torch.empty((b * t, self.latent_dim), dtype=torch.float32, device=x.device)
+        rec = torch.empty_like(xf)
+        hub = torch.zeros(2, dtype=torch.float64, device=x.device) if return_loss else None
+        _cabi.check(lib.wfk_convmodel_forward(xf.data_ptr(), b * t, c, self.latent_dim, arr, z.data_ptr(), rec.data_ptr(),
+                                              None if hub is None else hub.data_ptr(),
+                                              torch.cuda.current_stream(x.device).cuda_stream), "wfk_convmodel_forward")
+        if return_loss:
+            return z, rec, (hub[0] / hub[1]).to(torch.float32)
+        return z, rec
