@@ -9,7 +9,8 @@ import ctypes as C
 import os
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libwfk_b200.so"
+# WFK_LIB_PATH selects another build of the same ABI (same-box A/B runs of two kernel versions)
+_LIB_PATH = Path(os.environ.get("WFK_LIB_PATH") or (Path(__file__).resolve().parent / "libwfk_b200.so"))
 
 WFK_MAX_THRESHOLDS = 8
 WFK_NUM_POOLS = 3

@@ -651,13 +651,14 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
                 if (p.xform_debug != 1) {
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(h2[e]);
-                    const float vx = fmaf(f.x, ga[2 * e], gb[2 * e]);
-                    const float vy = fmaf(f.y, ga[2 * e + 1], gb[2 * e + 1]);
-                    float tx, ty;
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(vx));
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(vy));
-                    h2[e] = __floats2half2_rn(fmaf(vx, tx, vx), fmaf(vy, ty, vy));
+                    // packed fp32x2 FMAs (sm_100): same rounding per component, half the issue slots
+                    const float2 v = __ffma2_rn(__half22float2(h2[e]), make_float2(ga[2 * e], ga[2 * e + 1]),
+                                                make_float2(gb[2 * e], gb[2 * e + 1]));
+                    float2 t;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(v.x));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(v.y));
+                    const float2 y = __ffma2_rn(v, t, v);
+                    h2[e] = __floats2half2_rn(y.x, y.y);
                   }
                 }
                 sts_v4(addr[j], u[j]);
@@ -891,10 +892,14 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           for (int j = 0; j < 8; ++j) {
             const uint4 bu = lds_v4(b4 + 16 * j);
             const float4 b = make_float4(__uint_as_float(bu.x), __uint_as_float(bu.y), __uint_as_float(bu.z), __uint_as_float(bu.w));
-            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+            const float2 s01 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])),
+                                          make_float2(b.x, b.y));
+            const float2 s23 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
+                                          make_float2(b.z, b.w));
+            v[4 * j + 0] = s01.x;
+            v[4 * j + 1] = s01.y;
+            v[4 * j + 2] = s23.x;
+            v[4 * j + 3] = s23.y;
           }
         }
         if (has_res) {

@@ -52,10 +52,12 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  // back-off wait for the NON-critical waiters (epilogue / producers): sleep between probes instead of spinning
   uint32_t spins = 0;
   long long t0 = 0;
-  while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
-    if ((++spins & 63u) == 0) {
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(hint_ns);
+    if ((++spins & 1023u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 6000000000ll) __trap();
