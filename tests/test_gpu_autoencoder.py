@@ -254,3 +254,33 @@ def test_decode_run_to_run(model):
     a = model.decode(z)
     b = model.decode(z)
     assert rel_l2(a, b) < 1e-6
+
+
+@pytest.mark.parametrize("cfg_over", [
+    dict(block_out_channels=[64, 128], layers_per_block=1, norm_num_groups=16, latent_channels=4),
+    dict(block_out_channels=[128, 128, 256], layers_per_block=1, norm_num_groups=32, latent_channels=2, out_channels=2),
+])
+def test_other_autoencoder_configs_vs_oracle(cfg_over):
+    """The engine is not hard-wired to the Path-B config: other block widths / depths / group counts / latent and output
+    channel counts follow the same oracle (AutoencoderKL is built from config in every reference experiment)."""
+    from oracle import akl_oracle as O
+    from weatherforecastingtoolkit_b200.models.autoencoderkl import AutoencoderKL
+    from weatherforecastingtoolkit_b200.synthetic import PATHB_AKL_CONFIG, make_akl_state_dict
+    cfg = dict(PATHB_AKL_CONFIG)
+    cfg.update(cfg_over)
+    nb = len(cfg["block_out_channels"])
+    cfg["down_block_types"] = ["DownEncoderBlock2D"] * nb
+    cfg["up_block_types"] = ["UpDecoderBlock2D"] * nb
+    sd = make_akl_state_dict(cfg, seed=3, affine_jitter=0.1)
+    m = AutoencoderKL(**cfg)
+    m.load_state_dict(sd, strict=True)
+    torch.manual_seed(11)
+    x = torch.rand(2, 1, 64, 48)
+    with torch.no_grad():
+        mom = O.akl_encode_moments(x, sd, cfg)
+        lc = cfg["latent_channels"]
+        dec = O.akl_decode(mom[:, :lc].contiguous(), sd, cfg)
+    got_m = m.encode(x.to(DEV)).parameters
+    assert got_m.shape == mom.shape and rel_l2(got_m, mom) < 1e-2
+    got_d = m.decode(mom[:, :lc].contiguous().to(DEV))
+    assert got_d.shape == dec.shape and rel_l2(got_d, dec) < 1e-2

@@ -711,7 +711,8 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           tot += s_stats[wi * (BN / 2) + et];
           s_stats[wi * (BN / 2) + et] = 0.f;
         }
-        atomicAdd(&p.stats[(static_cast<int64_t>(frame) * p.groups_total + g) * 2 + (et & 1)], static_cast<double>(tot));
+        if (g < p.groups_total)   // N tail (n_total < BN): groups beyond the tensor only ever held zeros
+          atomicAdd(&p.stats[(static_cast<int64_t>(frame) * p.groups_total + g) * 2 + (et & 1)], static_cast<double>(tot));
       }
       named_bar_sync(1, kEpiThreads);
     };
@@ -1301,9 +1302,9 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   wfk::ConvKernelParams& p = plan->params;
   plan->bn = (d->n_total % 256 == 0 || d->n_total > 256) ? 256 : 128;
   plan->pair = (pair_mode_enabled() && wfk::g_num_sms % 2 == 0) ? 1 : 0;
-  if (d->stats != nullptr && d->n_total % plan->bn != 0) {
+  if (d->stats != nullptr && d->n_total % 32 != 0) {
     delete plan;
-    return wfk::fail(WFK_ERR_INVALID, "stats need n_total (%d) to be a multiple of the N tile (%d)", d->n_total, plan->bn);
+    return wfk::fail(WFK_ERR_INVALID, "stats need n_total (%d) to be a multiple of 32 (one accumulator chunk)", d->n_total);
   }
 
   // 128-pixel blocks per tile: MB per CTA, x2 for a CTA pair

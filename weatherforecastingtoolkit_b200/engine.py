@@ -643,7 +643,7 @@ class _Program:
         x = self.mid(x, "encoder.mid_block")
         _, h, w, c = x.shape
         out = torch.empty((n, 2 * eng.lc, h, w), dtype=torch.float32, device=self.dev)
-        if eng.fuse_gn and h >= 2 and "encoder.conv_out.w_folded" in t:
+        if eng.fuse_gn and h >= 2 and "encoder.conv_out.w_folded" in t and (2 * eng.lc) % 8 == 0:
             # conv_norm_out + SiLU fused into the halo staging, conv_out (+ folded quant_conv) on the tensor cores
             # (N padded to 8: a sliver of a 128-wide tile, still 5x faster than the CUDA-core gather), fp32 NHWC
             # result transposed to the NCHW moments tensor
@@ -664,8 +664,6 @@ class _Program:
             if eng.gn_inline:
                 self._gn_inline(d, x, "encoder.conv_norm_out")
             self._conv_plan(d, "encoder.gn+conv_out+quant_conv", 2.0 * n * h * w * (2 * eng.lc) * 9 * c)
-            if npad != 2 * eng.lc:
-                raise ValueError("moments channel count must be a multiple of 8 for the tensor-core tail")
             self._add(self.lib.wfk_nhwc_to_nchw_f32, (mom.data_ptr(), n, h * w, npad, out.data_ptr()), "moments->NCHW")
             self.keep.append((x.t, mom, tab))
             return out
