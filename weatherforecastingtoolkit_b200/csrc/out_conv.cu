@@ -29,7 +29,7 @@ constexpr int kOutThreads = 352;        // >= kOH*kOH = 324
 constexpr int kTcWarps = 7;                       // 21 m16-tiles of halo pixels per block = 3 rounds of 7 warps
 constexpr int kTcThreads = kTcWarps * 32;
 constexpr int kTcMTiles = (kOH * kOH + 15) / 16;  // 21
-constexpr int kTcMaxKSteps = 16;                  // C <= 256
+constexpr int kTcStrip = 4;                       // tiles along x per block
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -45,7 +45,7 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 }
 
 template <int KSTEPS>
-__global__ void __launch_bounds__(kTcThreads) gn_silu_conv3x3_c1_tc_kernel(
+__global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3x3_c1_tc_kernel(
     const __half* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, int h, int w, int groups, float eps, const float* __restrict__ wt, float bias,
     float* __restrict__ out) {
@@ -54,12 +54,12 @@ __global__ void __launch_bounds__(kTcThreads) gn_silu_conv3x3_c1_tc_kernel(
   extern __shared__ __align__(16) uint8_t s_raw[];
   float* s_a = reinterpret_cast<float*>(s_raw);        // [C]  (already halved: silu(z) = h + h*tanh(h), h = z/2)
   float* s_b = s_a + C;                                // [C]
-  float* s_d = s_b + C;                                // [kTcMTiles*16][9]
-  uint2* s_bf = reinterpret_cast<uint2*>(s_d + kTcMTiles * 16 * 9);   // [KSTEPS][2][32] weight fragments
+  float* s_d = s_b + C;                                // [2][kTcMTiles*16][9] (double-buffered per tile)
+  uint2* s_bf = reinterpret_cast<uint2*>(s_d + 2 * kTcMTiles * 16 * 9);   // [KSTEPS][2][32] weight fragments
   __half* s_t = reinterpret_cast<__half*>(s_bf + KSTEPS * 2 * 32);    // [kTcWarps][16][kPitch]
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.z;
-  const int x0 = blockIdx.x * kOT, y0 = blockIdx.y * kOT;
+  const int y0 = blockIdx.y * kOT;
   const int cpg = C / groups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < groups) {
@@ -101,11 +101,28 @@ __global__ void __launch_bounds__(kTcThreads) gn_silu_conv3x3_c1_tc_kernel(
   static_assert((16 * kChunks) % 32 == 0, "C must be a multiple of 16");
   __half* my_t = s_t + warp * 16 * kPitch;
   const uint32_t my_t_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(my_t));
-  for (int mt = warp; mt < kTcMTiles; mt += kTcWarps) {
-    // all of the m-tile's loads are issued before any of them is consumed (a load -> math -> store loop serialises
-    // kIters HBM round trips per tile and left the first version latency-bound)
-    uint4 u[kIters];
-    bool ok[kIters];
+  // every load of a lane hits the SAME 8-channel chunk (32 % kChunks == 0): its scale / shift pairs live in registers.
+  // (Re-reading them from shared memory per load was 4x the tile's own bytes and saturated the L1 / shared pipe.)
+  static_assert(32 % kChunks == 0 || kChunks == 32, "a lane's channel chunk must not depend on the load index");
+  float ga[8], gb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] = s_a[(lane % kChunks) * 8 + j];
+    gb[j] = s_b[(lane % kChunks) * 8 + j];
+  }
+  // A block walks a strip of kTcStrip tiles along x (prologue paid once); each warp owns m-tiles warp, warp+7, warp+14
+  // of every tile. The loads of the NEXT m-tile (possibly of the next tile) are in flight while the current one is
+  // transformed and multiplied: the m-tile chain is otherwise one HBM round trip long.
+  const int tiles_x = (w + kOT - 1) / kOT;
+  const int tx_first = blockIdx.x * kTcStrip;
+  const int ntiles = min(kTcStrip, tiles_x - tx_first);
+  constexpr int kPerTile = kTcMTiles / kTcWarps;   // 3
+  static_assert(kTcMTiles % kTcWarps == 0, "m-tiles must split evenly over the warps");
+  const int n_items = ntiles * kPerTile;
+  auto issue_loads = [&](const int item, uint4 (&u)[kIters], uint32_t& okmask) {
+    const int ts = item / kPerTile, mt = warp + kTcWarps * (item - ts * kPerTile);
+    const int x0 = (tx_first + ts) * kOT;
+    okmask = 0;
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
       const int idx = it * 32 + lane;
@@ -113,32 +130,31 @@ __global__ void __launch_bounds__(kTcThreads) gn_silu_conv3x3_c1_tc_kernel(
       const int q = mt * 16 + pl;
       const int qy = q / kOH, qx = q - qy * kOH;
       const int y = y0 + qy - 1, xx = x0 + qx - 1;
-      ok[it] = q < kOH * kOH && y >= 0 && y < h && xx >= 0 && xx < w;
+      if (q < kOH * kOH && y >= 0 && y < h && xx >= 0 && xx < w) okmask |= 1u << it;
       const int yc = min(max(y, 0), h - 1), xc = min(max(xx, 0), w - 1);   // clamped: the load itself is unconditional
       u[it] = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * h + yc) * w + xc) * C) + ck);
     }
+  };
+  auto process = [&](const int item, uint4 (&u)[kIters], const uint32_t okmask, float* sd) {
+    const int ts = item / kPerTile, mt = warp + kTcWarps * (item - ts * kPerTile);
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
       const int idx = it * 32 + lane;
       const int pl = idx / kChunks, ck = idx - pl * kChunks;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (ok[it]) {
+      if (okmask & (1u << it)) {
         v = u[it];
         __half2* h2 = reinterpret_cast<__half2*>(&v);
-        const float4 a0 = *reinterpret_cast<const float4*>(s_a + ck * 8), a1 = *reinterpret_cast<const float4*>(s_a + ck * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(s_b + ck * 8), b1 = *reinterpret_cast<const float4*>(s_b + ck * 8 + 4);
-        const float ga[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float gb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h2[e]);
-          const float v0 = fmaf(f.x, ga[2 * e], gb[2 * e]);
-          const float v1 = fmaf(f.y, ga[2 * e + 1], gb[2 * e + 1]);
-          float t0, t1;
-          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(v0));
-          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(v1));
-          h2[e] = __floats2half2_rn(fmaf(v0, t0, v0), fmaf(v1, t1, v1));
+          const float2 hv = __ffma2_rn(__half22float2(h2[e]), make_float2(ga[2 * e], ga[2 * e + 1]),
+                                       make_float2(gb[2 * e], gb[2 * e + 1]));
+          float2 tv;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(tv.x) : "f"(hv.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(tv.y) : "f"(hv.y));
+          const float2 yv = __ffma2_rn(hv, tv, hv);
+          h2[e] = __floats2half2_rn(yv.x, yv.y);
         }
       }
       *reinterpret_cast<uint4*>(my_t + pl * kPitch + ck * 8) = v;
@@ -161,21 +177,36 @@ __global__ void __launch_bounds__(kTcThreads) gn_silu_conv3x3_c1_tc_kernel(
       for (int j = 0; j < 4; ++j) {
         const int tap = nt * 8 + (lane & 3) * 2 + (j & 1);
         const int row = (lane >> 2) + ((j >> 1) << 3);
-        if (tap < 9) s_d[(mt * 16 + row) * 9 + tap] = acc[nt][j];
+        if (tap < 9) sd[(mt * 16 + row) * 9 + tap] = acc[nt][j];
       }
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < kOT * kOT; p += blockDim.x) {
-    const int py = p / kOT, pxx = p - py * kOT;
-    const int y = y0 + py, xx = x0 + pxx;
-    if (y < h && xx < w) {
-      float acc = bias;
+  };
+  // after a tile's m-tiles: block barrier, then the 9-tap gather from that tile's s_d buffer (double-buffered, so the
+  // next tile's m-tiles may already be written while stragglers still gather)
+  auto finish_tile = [&](const int ts, const float* sd) {
+    __syncthreads();
+    const int x0 = (tx_first + ts) * kOT;
+    for (int p = threadIdx.x; p < kOT * kOT; p += blockDim.x) {
+      const int py = p / kOT, pxx = p - py * kOT;
+      const int y = y0 + py, xx = x0 + pxx;
+      if (y < h && xx < w) {
+        float acc = bias;
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) acc += s_d[((py + r) * kOH + (pxx + s)) * 9 + r * 3 + s];
-      out[(static_cast<int64_t>(n) * h + y) * w + xx] = acc;
+          for (int s = 0; s < 3; ++s) acc += sd[((py + r) * kOH + (pxx + s)) * 9 + r * 3 + s];
+        out[(static_cast<int64_t>(n) * h + y) * w + xx] = acc;
+      }
     }
+  };
+  // single register buffer: with <= 72 registers four blocks (28 warps) fit an SM and thread-level parallelism hides the
+  // load latency better than a register double buffer at two blocks per SM did
+  uint4 u0[kIters];
+  uint32_t ok0 = 0;
+  for (int item = 0; item < n_items; ++item) {
+    const int ts = item / kPerTile;
+    issue_loads(item, u0, ok0);
+    process(item, u0, ok0, s_d + (ts & 1) * (kTcMTiles * 16 * 9));
+    if (item % kPerTile == kPerTile - 1) finish_tile(ts, s_d + (ts & 1) * (kTcMTiles * 16 * 9));
   }
 }
 
@@ -183,7 +214,7 @@ template <int KSTEPS>
 int launch_tail_tc(const __half* x, const double* stats, const float* gamma, const float* beta, int n, int h, int w,
                    int groups, float eps, const float* weight, float bias, float* out, cudaStream_t s) {
   constexpr int C = KSTEPS * 16;
-  const size_t smem = (2 * C + kTcMTiles * 16 * 9) * sizeof(float) + static_cast<size_t>(KSTEPS) * 2 * 32 * 8 +
+  const size_t smem = (2 * C + 2 * kTcMTiles * 16 * 9) * sizeof(float) + static_cast<size_t>(KSTEPS) * 2 * 32 * 8 +
                       static_cast<size_t>(kTcWarps) * 16 * (C + 8) * 2;
   static bool attr_set = false;
   if (!attr_set) {
@@ -192,7 +223,8 @@ int launch_tail_tc(const __half* x, const double* stats, const float* gamma, con
     if (e != cudaSuccess) return fail(WFK_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((w + kOT - 1) / kOT, (h + kOT - 1) / kOT, n);
+  const int tiles_x = (w + kOT - 1) / kOT;
+  dim3 grid((tiles_x + kTcStrip - 1) / kTcStrip, (h + kOT - 1) / kOT, n);
   gn_silu_conv3x3_c1_tc_kernel<KSTEPS><<<grid, kTcThreads, smem, s>>>(x, stats, gamma, beta, h, w, groups, eps, weight,
                                                                     bias, out);
   return launched("gn_silu_conv3x3_c1_tc_kernel");
