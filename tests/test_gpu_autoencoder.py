@@ -284,3 +284,24 @@ def test_other_autoencoder_configs_vs_oracle(cfg_over):
     assert got_m.shape == mom.shape and rel_l2(got_m, mom) < 1e-2
     got_d = m.decode(mom[:, :lc].contiguous().to(DEV))
     assert got_d.shape == dec.shape and rel_l2(got_d, dec) < 1e-2
+
+
+@pytest.mark.parametrize("h,w", [(16, 32), (64, 24), (136, 64)])
+def test_akl_ragged_sizes_vs_oracle(model, akl_weights, h, w):
+    """Sizes that are not multiples of the 16-pixel tiles (latents 2x4, 8x3, 17x8): partial tiles, single-tile frames,
+    halo boxes that are mostly out of the image. (The attention GEMMs need h*w of the latent to be a multiple of 8 --
+    16-byte rows of the probability matrix -- and the engine raises otherwise, which the last assertion pins.)"""
+    from oracle import akl_oracle as O
+    cfg, sd = akl_weights
+    torch.manual_seed(h * 100 + w)
+    x = torch.rand(2, 1, h, w)
+    with torch.no_grad():
+        m = O.akl_encode_moments(x, sd, cfg)
+        d = O.akl_decode(m[:, :4].contiguous(), sd, cfg)
+    got_m = model.encode(x.to(DEV)).parameters
+    assert got_m.shape == m.shape and rel_l2(got_m, m) < 1e-2, rel_l2(got_m, m)
+    got_d = model.decode(m[:, :4].contiguous().to(DEV))
+    assert got_d.shape == d.shape and rel_l2(got_d, d) < 1e-2, rel_l2(got_d, d)
+    if (h, w) == (16, 32):
+        with pytest.raises(ValueError):
+            model.encode(torch.rand(1, 1, 24, 40, device=DEV))  # latent 3x5 = 15 tokens: unsupported, loudly
