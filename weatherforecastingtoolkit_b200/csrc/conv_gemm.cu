@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
   // Row-contiguous (shared-memory staged) epilogue accesses: pays for the 128-wide tiles, whose K = 9*128 layers are
   // epilogue / LSU-bound; the 256-wide tiles keep direct row-per-lane accesses (their epilogue has 2-4x the MMA time
   // to hide in, and the extra staging traffic and the shallower operand ring cost more than the stores)
-  constexpr bool kCoalesce = (BN == 128);
+  constexpr bool kCoalesce = (BN == 128) || !HALO;
+  // fp32 outputs (attention scores) of the plain-tap kernels: the same staging with 128-byte rows
+  constexpr bool kCoalesceF32 = !HALO;
+  constexpr uint32_t kStageWarpBytes = HALO ? 2048u : 4096u;
   constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
   constexpr int kBBytes = kBRows * kBlockK * 2;
   constexpr int kCtas = PAIR ? 2 : 1;
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       fold_stats(frame, 0);
     };
     // swizzled staging offsets: this lane's OWN row (unit j) and the coalesced (row 8j + lane/4, unit lane & 3) slots
-    const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(ew) * 2048u;
+    const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(ew) * kStageWarpBytes;
     const uint32_t own_row = stg + static_cast<uint32_t>(lane) * 64u;
     const uint32_t own_x = static_cast<uint32_t>((lane >> 1) & 3);
     uint32_t co_off[4];
@@ -827,6 +830,30 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
               const int ox = px * p.out_sx + (t.phase & 1);
               const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
               cbase[mb][j] = pix * p.ldc + static_cast<int64_t>(t.nt) * BN + 8 * (lane & 3);
+            }
+          }
+        }
+      }
+      // fp32 output rows for the coalesced store: access i serves 16 bytes (unit lane & 7) of row 4*i + lane/8
+      int64_t fbase[kCoalesceF32 ? MB : 1][8];
+      uint32_t fvalid = 0;
+      if constexpr (kCoalesceF32) {
+        if (p.out_f != nullptr) {
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            const int blk = static_cast<int>(cta_rank) * MB + mb;
+            const int bx = p.stack_x ? t.tx * kBlocksPerTile + blk : t.tx;
+            const int by = p.stack_x ? t.ty : t.ty * kBlocksPerTile + blk;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = quarter * 32 + 4 * i + (lane >> 3);
+              const int py = by * bh + (rr >> p.bw_log2);
+              const int px = bx * bw + (rr & (bw - 1));
+              if (py < p.tile_h && px < p.tile_w) fvalid |= 1u << (mb * 8 + i);
+              const int oy = py * p.out_sy + (t.phase >> 1);
+              const int ox = px * p.out_sx + (t.phase & 1);
+              const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
+              fbase[mb][i] = pix * p.ldc + static_cast<int64_t>(t.nt) * BN + 4 * (lane & 7);
             }
           }
         }
@@ -993,8 +1020,30 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           }
           __syncwarp();
         }
-        if (valid) {
+        if constexpr (kCoalesceF32) {
           if (p.out_f != nullptr) {
+            // own row (32 floats = 8 units of 16 B, unit XOR-swizzled by the row) -> staging -> 4 rows x 128 B per store
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts_v4(stg + static_cast<uint32_t>(lane) * 128u + ((static_cast<uint32_t>(j) ^ (lane & 7u)) << 4),
+                     make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                __float_as_uint(v[4 * j + 3])));
+            __syncwarp();
+            if (c0 + 4 * (lane & 7) < ncols) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t rr = 4u * i + (lane >> 3);
+                const int64_t b_i = (MB == 1) ? fbase[0][i] : (mb ? fbase[MB - 1][i] : fbase[0][i]);
+                if (fvalid & (1u << (mb * 8 + i)))
+                  *reinterpret_cast<uint4*>(p.out_f + b_i + c0) =
+                      lds_v4(stg + rr * 128u + (((lane & 7u) ^ (rr & 7u)) << 4));
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if (valid) {
+          if (!kCoalesceF32 && p.out_f != nullptr) {
             float4* op = reinterpret_cast<float4*>(p.out_f + base + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -1074,19 +1123,19 @@ template <int BN, bool PAIR, bool HALO>
 struct ConvCfg;
 template <>
 struct ConvCfg<256, false, false> {
-  static constexpr int kMB = 1, kStages = 4;   // 48 KB / stage
+  static constexpr int kMB = 1, kStages = 3;   // 48 KB / stage (+ 32 KB epilogue staging)
 };
 template <>
 struct ConvCfg<128, false, false> {            // two pixel blocks share the weight tile
-  static constexpr int kMB = 2, kStages = 4;   // 48 KB / stage
+  static constexpr int kMB = 2, kStages = 3;   // 48 KB / stage (+ 32 KB epilogue staging)
 };
 template <>
 struct ConvCfg<256, true, false> {
-  static constexpr int kMB = 1, kStages = 6;   // 16 + 16 KB / stage
+  static constexpr int kMB = 1, kStages = 5;   // 16 + 16 KB / stage (+ 32 KB epilogue staging)
 };
 template <>
 struct ConvCfg<128, true, false> {
-  static constexpr int kMB = 2, kStages = 5;   // 32 + 8 KB / stage
+  static constexpr int kMB = 2, kStages = 4;   // 32 + 8 KB / stage (+ 32 KB epilogue staging)
 };
 template <>
 struct ConvCfg<256, true, true> {
@@ -1105,7 +1154,7 @@ constexpr size_t conv_smem_bytes() {
   constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + (Cfg::kMB == 1 ? 6 : 5) * b_bytes
                                : Cfg::kStages * (Cfg::kMB * kABytes + b_bytes);
   return 1024 /*align slack*/ + ring + (3 * Cfg::kStages + 2 * kHaloBStagesMax + 4) * 8 + 16 +
-         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + (BN == 128 ? kEpiWarps * 2048 : 0) + 64;
+         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + ((BN == 128 || !HALO) ? kEpiWarps * (HALO ? 2048 : 4096) : 0) + 64;
 }
 
 template <int BN, bool PAIR, bool HALO, bool EPI = false>
