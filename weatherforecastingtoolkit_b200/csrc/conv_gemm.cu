@@ -207,10 +207,15 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
   // Row-contiguous (shared-memory staged) epilogue accesses: pays for the 128-wide tiles, whose K = 9*128 layers are
   // epilogue / LSU-bound; the 256-wide tiles keep direct row-per-lane accesses (their epilogue has 2-4x the MMA time
   // to hide in, and the extra staging traffic and the shallower operand ring cost more than the stores)
-  constexpr bool kCoalesce = (BN == 128) || !HALO;
+  constexpr bool kCoalesce = true;
+  // The 256-wide HALO kernel has ~10 KB of shared memory to spare: its staging tile holds 16 rows and a chunk goes
+  // through it in two passes (rows 0-15, rows 16-31); every other kernel stages all 32 rows at once.
+  constexpr int kStPasses = (HALO && BN == 256) ? 2 : 1;
+  constexpr int kStRows = 32 / kStPasses;
+  constexpr int kStAcc = 4 / kStPasses;            // coalesced accesses (8 rows x 64 B each) per pass
   // fp32 outputs (attention scores) of the plain-tap kernels: the same staging with 128-byte rows
   constexpr bool kCoalesceF32 = !HALO;
-  constexpr uint32_t kStageWarpBytes = HALO ? 2048u : 4096u;
+  constexpr uint32_t kStageWarpBytes = HALO ? 2048u / kStPasses : 4096u;
   constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
   constexpr int kBBytes = kBRows * kBlockK * 2;
   constexpr int kCtas = PAIR ? 2 : 1;
@@ -225,7 +230,8 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
   constexpr int kXfPasses = (kHaloPitch * kHaloRows + kXfRowsPerPass - 1) / kXfRowsPerPass;
   constexpr int kXfGroup = 6;                      // loads in flight per thread (MB=2: 11 passes = 6 + 5; MB=1: 12 = 6 + 6)
   constexpr int kStageBytes = HALO ? kHaloStage : MB * kABytes + kBBytes;
-  constexpr int kBStages = HALO ? (MB == 1 ? 6 : 5) : 0;  // weight-tile ring depth (16 KB / 8 KB tiles)
+  constexpr int kBStages = HALO ? (MB == 1 ? (EPI ? 5 : 6) : 5) : 0;  // weight-tile ring depth (16 KB / 8 KB tiles; the EPI
+                                                                      // variant gives one up for its scale2 / shift2 arrays)
   // Warp roles by warp id. The SM's warp arbiter favours HIGHER warp ids, so the latency-critical
   // single-thread roles sit at the top: (HALO: transform 0..3,) epilogue (8 warps), (HALO: weight-tile
   // TMA,) activation TMA, then the MMA issuer last. The epilogue outranks the transform: with K = 9*128
@@ -745,8 +751,9 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
     };
     // swizzled staging offsets: this lane's OWN row (unit j) and the coalesced (row 8j + lane/4, unit lane & 3) slots
     const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(ew) * kStageWarpBytes;
-    const uint32_t own_row = stg + static_cast<uint32_t>(lane) * 64u;
+    const uint32_t own_row = stg + static_cast<uint32_t>(lane & (kStRows - 1)) * 64u;
     const uint32_t own_x = static_cast<uint32_t>((lane >> 1) & 3);
+    const int own_pass = lane / kStRows;           // the pass in which this lane's own row sits in the staging tile
     uint32_t co_off[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -935,11 +942,16 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           if constexpr (kCoalesce) {
             // coalesced pieces -> staging -> this lane's own row
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sts_v4(co_off[j], rcur[j]);
-            __syncwarp();
+            for (int ps = 0; ps < kStPasses; ++ps) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rrow[j] = lds_v4(own_row + ((static_cast<uint32_t>(j) ^ own_x) << 4));
-            __syncwarp();
+              for (int j = 0; j < kStAcc; ++j) sts_v4(co_off[j], rcur[ps * kStAcc + j]);
+              __syncwarp();
+              if (kStPasses == 1 || own_pass == ps) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rrow[j] = lds_v4(own_row + ((static_cast<uint32_t>(j) ^ own_x) << 4));
+              }
+              __syncwarp();
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) rrow[j] = rcur[j];
@@ -1002,23 +1014,30 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
             }
           }
         } else if (p.out_h != nullptr && p.xform_debug != 32) {   // 32: timing experiment without the fp16 stores
+          uint4 up[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            __half2* h2 = reinterpret_cast<__half2*>(&u);
+            __half2* h2 = reinterpret_cast<__half2*>(&up[j]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-            sts_v4(own_row + ((static_cast<uint32_t>(j) ^ own_x) << 4), u);
           }
-          __syncwarp();
-          if (c0 + 8 * (lane & 3) < ncols) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int64_t b_j = (MB == 1) ? cbase[0][j] : (mb ? cbase[MB - 1][j] : cbase[0][j]);
-              if (cvalid & (1u << (mb * 4 + j))) *reinterpret_cast<uint4*>(p.out_h + b_j + c0) = lds_v4(co_off[j]);
+          for (int ps = 0; ps < kStPasses; ++ps) {
+            if (kStPasses == 1 || own_pass == ps) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) sts_v4(own_row + ((static_cast<uint32_t>(j) ^ own_x) << 4), up[j]);
             }
+            __syncwarp();
+            if (c0 + 8 * (lane & 3) < ncols) {
+#pragma unroll
+              for (int j = 0; j < kStAcc; ++j) {
+                const int jj = ps * kStAcc + j;
+                const int64_t b_j = (MB == 1) ? cbase[0][jj] : (mb ? cbase[MB - 1][jj] : cbase[0][jj]);
+                if (cvalid & (1u << (mb * 4 + jj))) *reinterpret_cast<uint4*>(p.out_h + b_j + c0) = lds_v4(co_off[j]);
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         if constexpr (kCoalesceF32) {
           if (p.out_f != nullptr) {
@@ -1151,10 +1170,10 @@ constexpr size_t conv_smem_bytes() {
   using Cfg = ConvCfg<BN, PAIR, HALO>;
   constexpr size_t b_bytes = static_cast<size_t>(PAIR ? BN / 2 : BN) * kBlockK * 2;
   constexpr size_t halo_stage = (static_cast<size_t>(8 * Cfg::kMB + 2) * kHaloRows * 128 + 1023) & ~static_cast<size_t>(1023);
-  constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + (Cfg::kMB == 1 ? 6 : 5) * b_bytes
+  constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + (Cfg::kMB == 1 ? (EPI ? 5 : 6) : 5) * b_bytes
                                : Cfg::kStages * (Cfg::kMB * kABytes + b_bytes);
   return 1024 /*align slack*/ + ring + (3 * Cfg::kStages + 2 * kHaloBStagesMax + 4) * 8 + 16 +
-         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + ((BN == 128 || !HALO) ? kEpiWarps * (HALO ? 2048 : 4096) : 0) + 64;
+         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + kEpiWarps * (HALO ? (BN == 256 ? 1024 : 2048) : 4096) + 64;
 }
 
 template <int BN, bool PAIR, bool HALO, bool EPI = false>
