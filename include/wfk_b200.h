@@ -59,6 +59,11 @@ int wfk_stage_vil_u8(const uint8_t* nhwt, int n, int h, int w, int t, void* out_
 int wfk_stage_vil_windows(const uint8_t* events, int num_events, int h, int w, int t_raw, const int32_t* windows, int n,
                           int t, void* out_ntchw, int out_dtype, void* stream);
 
+/*     Same with the rescale constants of preprocess_data_dict spelled out: out = fl32(scale) * ((float)u8 + fl32(offset))
+ *     -- rescale '01' = (1/255, 0), rescale 'sevir' = (1/47.54, -33.44) (sevir.py:44-63, 640-662). */
+int wfk_stage_vil_windows_ex(const uint8_t* events, int num_events, int h, int w, int t_raw, const int32_t* windows, int n,
+                             int t, float scale, float offset, void* out_ntchw, int out_dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a8  Latent predictor.  Replaces the residual framing + nn.Linear(13*C, 12*C) + permutes of
  *     Model.validation_step (experiments/v1_experiments/pretrained_ae_linear_sevir/train.py:
@@ -329,6 +334,26 @@ int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const float* gamm
  * Replaces torch.softmax(attention_scores.float(), dim=-1) (attention.py:171); `scale` is the
  * baddbmm alpha (attention.py:148, 168). */
 int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, void* stream);
+
+/* f.4  ConvAttnModel latent compressor (experiments/v1_experiments/pretrained_ae_convattn_ae_sevir/train.py:58-170),
+ *      whole network in one launch, one CTA per latent frame: x [n, cin, 48, 48] fp32 -> z [n, latent_dim] and
+ *      recon [n, cin, 48, 48]; huber_sums (optional, double[2]) += (sum of HuberLoss(recon, x) terms, element count)
+ *      as in the experiment's validation_step (train.py:206-209).  mode 0: encode + decode (forward), 1: encode only
+ *      (z written), 2: decode only (z read; x may be NULL).  Fixed by the kernel: 48 x 48 input, embed 128, 8 heads,
+ *      feed-forward 512; runtime: cin <= 8, layers <= 8, latent_dim <= 512.  weights: 28 + 30 * layers DEVICE fp32
+ *      pointers, 16-byte aligned, in the order listed in predictors.py (ConvAttnModel._weight_pointers). */
+int wfk_convattn_forward(const float* x, int n, int cin, int layers, int latent_dim, const float* const* weights,
+                         int num_weights, float* z, float* recon, double* huber_sums, int mode, void* stream);
+
+/* f.3  Validation panels.  Replaces the numpy + matplotlib colour mapping of log_wandb_images
+ *      (pipeline/helpers.py:155-225) with vil_cmap() (pipeline/datasets/sevir/sevir.py:1237-1268):
+ *        tgt_u8 = (uint8)(clamp(tgt,0,1) * 255), pred_u8 likewise (truncation), diff_u8 = |tgt_u8 - pred_u8|,
+ *        tgt_rgba = lut_vil[tgt_u8], pred_rgba = lut_vil[pred_u8], diff_rgba = lut_diff[diff_u8].
+ *      pred, tgt: DEVICE fp32 [count]; lut_*: DEVICE uint8 [256][4]; outputs DEVICE uint8 [count] / [count][4], each
+ *      may be NULL.  One pass, HBM-bound (8 B read + 15 B written per pixel). */
+int wfk_render_panels(const float* pred, const float* tgt, int64_t count, const uint8_t* lut_vil_rgba,
+                      const uint8_t* lut_diff_rgba, uint8_t* tgt_u8, uint8_t* pred_u8, uint8_t* diff_u8,
+                      uint8_t* tgt_rgba, uint8_t* pred_rgba, uint8_t* diff_rgba, void* stream);
 
 /* a7  DiagonalGaussianDistribution arithmetic (pipeline/models/autoencoderkl/distributions.py:26-42) in one pass:
  * moments [n, 2*lc, hw] fp32 -> logvar = clamp(moments[:, lc:], -30, 20), std = exp(0.5*logvar), var = exp(logvar)

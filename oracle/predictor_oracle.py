@@ -76,3 +76,61 @@ def convmodel_forward(x, sd):
                    f"decoder.{name}.1")
     y = F.conv2d(y, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
     return z, y.reshape(b, t, c, h, w)
+
+
+def _mha(q_in, kv_in, sd, p, nhead):
+    """nn.MultiheadAttention(batch_first=True) forward without masks: packed in_proj, heads of E/nhead, q scaled by
+    1/sqrt(dh), softmax, out_proj."""
+    e = q_in.shape[-1]
+    w, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
+    q = F.linear(q_in, w[:e], b[:e])
+    k = F.linear(kv_in, w[e:2 * e], b[e:2 * e])
+    v = F.linear(kv_in, w[2 * e:], b[2 * e:])
+    bsz, tq, tk, dh = q.shape[0], q.shape[1], k.shape[1], e // nhead
+    q = q.reshape(bsz, tq, nhead, dh).transpose(1, 2) * (dh ** -0.5)
+    k = k.reshape(bsz, tk, nhead, dh).transpose(1, 2)
+    v = v.reshape(bsz, tk, nhead, dh).transpose(1, 2)
+    att = torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v
+    att = att.transpose(1, 2).reshape(bsz, tq, e)
+    return F.linear(att, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+
+
+def convattn_forward(x, sd, nhead: int = 8):
+    """``ConvAttnModel.forward`` (experiments/v1_experiments/pretrained_ae_convattn_ae_sevir/train.py:131-163) restated on
+    a state_dict: encoder_cnn (:69-76), pre-norm nn.TransformerEncoderLayer stack (:79-86), attention pooling (:89-91,
+    137-138), encoder_head (:93-96), decoder_head + learned queries (:98-101, 147-150), pre-norm
+    nn.TransformerDecoderLayer stack (:103-110), decoder_cnn (:112-117). x [B, 4, 48, 48] -> (z [B, latent], recon)."""
+    def ln(v, p):
+        return F.layer_norm(v, (v.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+
+    def ff(v, p):
+        return F.linear(F.gelu(F.linear(v, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
+                        sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
+    b = x.shape[0]
+    y = F.conv2d(x, sd["encoder_cnn.0.weight"], sd["encoder_cnn.0.bias"], stride=2, padding=1)
+    y = F.gelu(F.group_norm(y, 8, sd["encoder_cnn.1.weight"], sd["encoder_cnn.1.bias"], 1e-5))
+    y = F.conv2d(y, sd["encoder_cnn.3.weight"], sd["encoder_cnn.3.bias"], stride=2, padding=1)
+    y = F.gelu(F.group_norm(y, 8, sd["encoder_cnn.4.weight"], sd["encoder_cnn.4.bias"], 1e-5))
+    t = y.flatten(2).transpose(1, 2) + sd["encoder_pos_embedding"]
+    layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("encoder_tf.layers."))
+    for l in range(layers):
+        p = f"encoder_tf.layers.{l}"
+        h = ln(t, p + ".norm1")
+        t = t + _mha(h, h, sd, p + ".self_attn", nhead)
+        t = t + ff(ln(t, p + ".norm2"), p)
+    pooled = _mha(sd["pooling_query"].expand(b, -1, -1), t, sd, "attention_pool", nhead)
+    z = F.linear(ln(pooled, "encoder_head.0"), sd["encoder_head.1.weight"], sd["encoder_head.1.bias"]).squeeze(1)
+    ctx = F.linear(z, sd["decoder_head.weight"], sd["decoder_head.bias"]).unsqueeze(1)
+    t = (sd["decoder_queries"] + sd["decoder_pos_embedding"]).expand(b, -1, -1)
+    for l in range(layers):
+        p = f"decoder_tf.layers.{l}"
+        h = ln(t, p + ".norm1")
+        t = t + _mha(h, h, sd, p + ".self_attn", nhead)
+        t = t + _mha(ln(t, p + ".norm2"), ctx, sd, p + ".multihead_attn", nhead)
+        t = t + ff(ln(t, p + ".norm3"), p)
+    e = t.shape[-1]
+    y = t.transpose(1, 2).reshape(b, e, 12, 12)
+    y = F.conv_transpose2d(y, sd["decoder_cnn.0.weight"], sd["decoder_cnn.0.bias"], stride=2, padding=1)
+    y = F.gelu(F.group_norm(y, 8, sd["decoder_cnn.1.weight"], sd["decoder_cnn.1.bias"], 1e-5))
+    y = F.conv_transpose2d(y, sd["decoder_cnn.3.weight"], sd["decoder_cnn.3.bias"], stride=2, padding=1)
+    return z, y

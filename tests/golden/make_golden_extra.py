@@ -216,6 +216,46 @@ def gen_convmodel(out):
     out["convmodel_huber"] = np.array(loss.item())
 
 
+CONVATTN_SCRIPT = "experiments/v1_experiments/pretrained_ae_convattn_ae_sevir/train.py"
+
+
+def convattn_case(seed=0, b=3, layers=4, latent_dim=512):
+    """(state_dict, latents [b, 4, 48, 48]): kaiming-normal matrices like ConvAttnModel.init_weights (train.py:121-129),
+    N(0,1) embeddings / queries like the constructor, random (non-trivial) norm affine parameters and biases."""
+    from weatherforecastingtoolkit_b200.predictors import ConvAttnModel as Mine
+    torch.manual_seed(4321 + seed)
+    m = Mine(num_tf_layers=layers, latent_dim=latent_dim)
+    sd = {}
+    for k, v in m.state_dict().items():
+        g = torch.Generator().manual_seed(S._name_seed("convattn." + k, seed))
+        leaf = k.rsplit(".", 1)[-1]
+        if v.ndim >= 2 and leaf in ("weight", "in_proj_weight"):
+            fan_in = int(np.prod(v.shape[1:]))
+            sd[k] = torch.randn(v.shape, generator=g) * float(np.sqrt(2.0 / fan_in))
+        elif v.ndim == 3:                                   # pos embeddings, queries
+            sd[k] = torch.randn(v.shape, generator=g)
+        elif leaf == "weight":                              # LayerNorm / GroupNorm scale
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+    g = torch.Generator().manual_seed(S._name_seed("convattn.x", seed))
+    x = torch.randn((b, 4, 48, 48), generator=g)
+    return sd, x
+
+
+def gen_convattn(out):
+    ns = ref_script_classes(CONVATTN_SCRIPT, ["ConvAttnModel"])
+    sd, x = convattn_case()
+    m = ns["ConvAttnModel"]().eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        z, rec = m(x)
+        loss = torch.nn.HuberLoss()(rec, x)
+    out["convattn_z"] = z.numpy()
+    out["convattn_recon"] = rec.numpy()
+    out["convattn_huber"] = np.array(loss.item())
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     out = {}
@@ -226,7 +266,7 @@ def main():
     print("wrote extra_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
-EXTRA_GENERATORS = [gen_discriminator, gen_posaware, gen_vit, gen_convmodel]
+EXTRA_GENERATORS = [gen_discriminator, gen_posaware, gen_vit, gen_convmodel, gen_convattn]
 
 if __name__ == "__main__":
     main()

@@ -1,7 +1,8 @@
 // VIL frame staging: uint8 NHWT (SEVIR on-disk layout) -> normalised float N T (C=1) H W.
 // Replaces SEVIRDataLoader.preprocess_data_dict + change_layout (reference
 // pipeline/datasets/sevir/sevir.py:626-666, 88-101; cast at :587-592), bit-exactly:
-//   out = fl32(1/255) * ((float)u8 + 0)
+//   out = fl32(scale) * ((float)u8 + fl32(offset))      rescale '01': scale = 1/255, offset = 0 (sevir.py:54-63);
+//                                                        rescale 'sevir': scale = 1/47.54, offset = -33.44 (:44-53)
 // HBM-bound: 128-bit loads of the byte stream into shared memory (the T=25 innermost bytes are
 // not 16-byte aligned per pixel, so the transpose happens in smem), 128-bit stores per frame plane.
 #include <cuda_fp16.h>
@@ -11,13 +12,15 @@
 namespace wfk {
 
 constexpr int kStagePix = 512;  // pixels per block
+constexpr float kScale01 = 1.0f / 255.0f;  // == fl32(1/255) = 0x3b808081
 
 // `windows` (optional): per output sequence (event index, first raw frame) into an event tensor [E, hw, t_src]
 // (SEVIR events hold t_src = 49 frames; a sequence is the slice [t0, t0 + t), sevir.py:851-889). Without it the
 // input is the already-sliced batch [n, hw, t] (t_src == t, t0 == 0).
 template <bool HALF_OUT>
 __global__ void __launch_bounds__(256) stage_vil_kernel(const uint8_t* __restrict__ in, int hw, int t, int t_src,
-                                                        const int32_t* __restrict__ windows, void* __restrict__ out) {
+                                                        const int32_t* __restrict__ windows, float scale, float offset,
+                                                        void* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t s_bytes[];  // [kStagePix * t_src]
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * kStagePix;
@@ -36,7 +39,6 @@ __global__ void __launch_bounds__(256) stage_vil_kernel(const uint8_t* __restric
     for (int i = threadIdx.x; i < nbytes; i += blockDim.x) s_bytes[i] = src[i];
   }
   __syncthreads();
-  const float scale = 1.0f / 255.0f;  // == fl32(1/255) = 0x3b808081
   // thread -> (frame index tq, group of 4 consecutive pixels pg)
   const int groups = (npix + 3) >> 2;
   for (int item = threadIdx.x; item < groups * t; item += blockDim.x) {
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(256) stage_vil_kernel(const uint8_t* __restric
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = pg + j;
-      v[j] = (p < npix) ? __fmul_rn(static_cast<float>(s_bytes[p * t_src + t0 + ti]), scale) : 0.f;
+      v[j] = (p < npix) ? __fmul_rn(__fadd_rn(static_cast<float>(s_bytes[p * t_src + t0 + ti]), offset), scale) : 0.f;
     }
     const int64_t o = (static_cast<int64_t>(n) * t + ti) * hw + p0 + pg;
     if (pg + 3 < npix && ((o & 3) == 0)) {
@@ -79,13 +81,14 @@ extern "C" int wfk_stage_vil_u8(const uint8_t* nhwt, int n, int h, int w, int t,
   dim3 grid((hw + wfk::kStagePix - 1) / wfk::kStagePix, n);
   const size_t smem = static_cast<size_t>(wfk::kStagePix) * t;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (out_dtype == 1) wfk::stage_vil_kernel<true><<<grid, 256, smem, s>>>(nhwt, hw, t, t, nullptr, out_ntchw);
-  else wfk::stage_vil_kernel<false><<<grid, 256, smem, s>>>(nhwt, hw, t, t, nullptr, out_ntchw);
+  if (out_dtype == 1) wfk::stage_vil_kernel<true><<<grid, 256, smem, s>>>(nhwt, hw, t, t, nullptr, wfk::kScale01, 0.f, out_ntchw);
+  else wfk::stage_vil_kernel<false><<<grid, 256, smem, s>>>(nhwt, hw, t, t, nullptr, wfk::kScale01, 0.f, out_ntchw);
   return wfk::launched("stage_vil_kernel");
 }
 
-extern "C" int wfk_stage_vil_windows(const uint8_t* events, int num_events, int h, int w, int t_raw, const int32_t* windows,
-                                     int n, int t, void* out_ntchw, int out_dtype, void* stream) {
+extern "C" int wfk_stage_vil_windows_ex(const uint8_t* events, int num_events, int h, int w, int t_raw, const int32_t* windows,
+                                        int n, int t, float scale, float offset, void* out_ntchw, int out_dtype,
+                                        void* stream) {
   WFK_REQUIRE_INIT();
   WFK_REQUIRE(events && windows && out_ntchw, "null pointer");
   WFK_REQUIRE(num_events > 0 && n > 0 && n <= 65535 && h > 0 && w > 0, "unsupported shape");
@@ -95,7 +98,13 @@ extern "C" int wfk_stage_vil_windows(const uint8_t* events, int num_events, int 
   dim3 grid((hw + wfk::kStagePix - 1) / wfk::kStagePix, n);
   const size_t smem = static_cast<size_t>(wfk::kStagePix) * t_raw;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (out_dtype == 1) wfk::stage_vil_kernel<true><<<grid, 256, smem, s>>>(events, hw, t, t_raw, windows, out_ntchw);
-  else wfk::stage_vil_kernel<false><<<grid, 256, smem, s>>>(events, hw, t, t_raw, windows, out_ntchw);
+  if (out_dtype == 1) wfk::stage_vil_kernel<true><<<grid, 256, smem, s>>>(events, hw, t, t_raw, windows, scale, offset, out_ntchw);
+  else wfk::stage_vil_kernel<false><<<grid, 256, smem, s>>>(events, hw, t, t_raw, windows, scale, offset, out_ntchw);
   return wfk::launched("stage_vil_kernel(windows)");
+}
+
+extern "C" int wfk_stage_vil_windows(const uint8_t* events, int num_events, int h, int w, int t_raw, const int32_t* windows,
+                                     int n, int t, void* out_ntchw, int out_dtype, void* stream) {
+  return wfk_stage_vil_windows_ex(events, num_events, h, w, t_raw, windows, n, t, wfk::kScale01, 0.f, out_ntchw, out_dtype,
+                                  stream);
 }

@@ -240,3 +240,117 @@ class ConvModel(nn.Module):
         if return_loss:
             return z, rec, (hub[0] / hub[1]).to(torch.float32)
         return z, rec
+
+
+class ConvAttnModel(nn.Module):
+    """``ConvAttnModel`` (experiments/v1_experiments/pretrained_ae_convattn_ae_sevir/train.py:58-163): same constructor,
+    module tree and ``state_dict`` keys (the torch modules are parameter containers, so a reference checkpoint loads with
+    ``strict=True``); ``encode`` / ``decode`` / ``forward`` run ONE kernel (``wfk_convattn_forward``), one CTA per frame."""
+
+    def __init__(self, in_channels=4, transformer_embed_dim=128, nhead=8, num_tf_layers=4, latent_dim=512):
+        super().__init__()
+        if transformer_embed_dim != 128 or nhead != 8:
+            raise ValueError("the fused kernel is built for transformer_embed_dim=128, nhead=8 (the reference's only use)")
+        if not (1 <= num_tf_layers <= 8 and 4 <= latent_dim <= 512 and 1 <= in_channels <= 8):
+            raise ValueError("supported: 1..8 layers, latent_dim 4..512, in_channels 1..8")
+        e = transformer_embed_dim
+        self.transformer_embed_dim, self.in_channels, self.latent_dim, self.num_tf_layers = e, in_channels, latent_dim, num_tf_layers
+        self.encoder_cnn = nn.Sequential(
+            nn.Conv2d(in_channels, 64, kernel_size=3, stride=2, padding=1), nn.GroupNorm(8, 64), nn.GELU(),
+            nn.Conv2d(64, e, kernel_size=3, stride=2, padding=1), nn.GroupNorm(8, e), nn.GELU())
+        self.encoder_pos_embedding = nn.Parameter(torch.randn(1, 144, e))
+        enc_layer = nn.TransformerEncoderLayer(d_model=e, nhead=nhead, dim_feedforward=e * 4, activation='gelu',
+                                               batch_first=True, norm_first=True)
+        self.encoder_tf = nn.TransformerEncoder(enc_layer, num_layers=num_tf_layers, enable_nested_tensor=False)
+        self.pooling_query = nn.Parameter(torch.randn(1, 1, e))
+        self.attention_pool = nn.MultiheadAttention(embed_dim=e, num_heads=nhead, batch_first=True)
+        self.encoder_head = nn.Sequential(nn.LayerNorm(e), nn.Linear(e, latent_dim))
+        self.decoder_head = nn.Linear(latent_dim, e)
+        self.decoder_queries = nn.Parameter(torch.randn(1, 144, e))
+        self.decoder_pos_embedding = nn.Parameter(torch.randn(1, 144, e))
+        dec_layer = nn.TransformerDecoderLayer(d_model=e, nhead=nhead, dim_feedforward=e * 4, activation='gelu',
+                                               batch_first=True, norm_first=True)
+        self.decoder_tf = nn.TransformerDecoder(dec_layer, num_layers=num_tf_layers)
+        self.decoder_cnn = nn.Sequential(
+            nn.ConvTranspose2d(e, 64, kernel_size=4, stride=2, padding=1), nn.GroupNorm(8, 64), nn.GELU(),
+            nn.ConvTranspose2d(64, in_channels, kernel_size=4, stride=2, padding=1))
+        self.apply(self.init_weights)
+        self._packed = None
+
+    def init_weights(self, m):
+        if isinstance(m, (nn.Linear, nn.Conv2d, nn.ConvTranspose2d)):
+            nn.init.kaiming_normal_(m.weight, nonlinearity='relu')
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, (nn.LayerNorm, nn.GroupNorm)):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+    def _weight_pointers(self):
+        """Parameters in the order ``wfk_convattn_forward`` reads them (28 + 30 * layers tensors)."""
+        def attn(a):
+            return [a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias]
+
+        def wb(*mods):
+            return [p for m in mods for p in (m.weight, m.bias)]
+        ec, dc = self.encoder_cnn, self.decoder_cnn
+        out = wb(ec[0], ec[1], ec[3], ec[4]) + [self.encoder_pos_embedding]
+        for l in self.encoder_tf.layers:
+            out += attn(l.self_attn) + wb(l.linear1, l.linear2, l.norm1, l.norm2)
+        out += [self.pooling_query] + attn(self.attention_pool) + wb(self.encoder_head[0], self.encoder_head[1])
+        out += wb(self.decoder_head) + [self.decoder_queries, self.decoder_pos_embedding]
+        for l in self.decoder_tf.layers:
+            out += attn(l.self_attn) + attn(l.multihead_attn) + wb(l.linear1, l.linear2, l.norm1, l.norm2, l.norm3)
+        return out + wb(dc[0], dc[1], dc[3])
+
+    def _pack(self, device):
+        params = self._weight_pointers()
+        key = (str(device), sum(p._version for p in params), tuple(p.data_ptr() for p in params))
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[1]
+        import ctypes as C
+        tensors = [p.detach().to(device=device, dtype=torch.float32).contiguous() for p in params]
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        self._packed = (key, (tensors, arr))
+        return self._packed[1]
+
+    def _run(self, x, z, mode, return_loss=False):
+        dev = x.device if x is not None else z.device
+        if dev.type != "cuda":
+            raise RuntimeError("this path runs on a B200 only (no CPU fallback): pass CUDA tensors")
+        lib = _cabi.init(dev.index if dev.index is not None else 0)
+        tensors, arr = self._pack(dev)
+        if x is not None:
+            if x.ndim != 4 or tuple(x.shape[1:]) != (self.in_channels, 48, 48):
+                raise ValueError(f"expected [B, {self.in_channels}, 48, 48] latents (144 positional embeddings), got {tuple(x.shape)}")
+            x = x.detach().to(torch.float32).contiguous()
+            n = x.shape[0]
+            z = torch.empty((n, self.latent_dim), dtype=torch.float32, device=dev)
+        else:
+            if z.ndim != 2 or z.shape[1] != self.latent_dim:
+                raise ValueError(f"expected [B, {self.latent_dim}] latents, got {tuple(z.shape)}")
+            z = z.detach().to(torch.float32).contiguous()
+            n = z.shape[0]
+        rec = torch.empty((n, self.in_channels, 48, 48), dtype=torch.float32, device=dev) if mode != 1 else None
+        hub = torch.zeros(2, dtype=torch.float64, device=dev) if return_loss else None
+        _cabi.check(lib.wfk_convattn_forward(None if x is None else x.data_ptr(), n, self.in_channels, self.num_tf_layers,
+                                             self.latent_dim, arr, len(tensors), z.data_ptr(),
+                                             None if rec is None else rec.data_ptr(), None if hub is None else hub.data_ptr(),
+                                             mode, torch.cuda.current_stream(dev).cuda_stream), "wfk_convattn_forward")
+        return z, rec, (None if hub is None else (hub[0] / hub[1]).to(torch.float32))
+
+    @torch.no_grad()
+    def encode(self, x):
+        """[b, 4, 48, 48] -> [b, latent_dim] (train.py:127-140)."""
+        return self._run(x, None, 1)[0]
+
+    @torch.no_grad()
+    def decode(self, z):
+        """[b, latent_dim] -> [b, 4, 48, 48] (train.py:142-156)."""
+        return self._run(None, z, 2)[1]
+
+    @torch.no_grad()
+    def forward(self, x, return_loss: bool = False):
+        """-> (z, out) (train.py:158-165); with ``return_loss`` also ``nn.HuberLoss()(out, x)`` (train.py:172, 206-209)."""
+        z, rec, loss = self._run(x, None, 0, return_loss)
+        return (z, rec, loss) if return_loss else (z, rec)

@@ -167,6 +167,13 @@ def make_predictor_params(in_frames: int = INPUT_FRAMES, pred_frames: int = PRED
     return w.float(), b.float()
 
 
+def make_loader_events(e: int, h: int, w: int, t_raw: int = 49, seed: int = 7) -> torch.Tensor:
+    """uint8 stand-in for a SEVIR HDF5 'vil' dataset [E, H, W, raw_seq_len] (sevir.py:562-566): iid bytes, so every
+    window of every event is distinguishable in the loader tests."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (e, h, w, t_raw), generator=g, dtype=torch.uint8)
+
+
 def make_vil_sequences(n: int, h: int = 384, w: int = 384, t: int = 25, seed: int = 1,
                        kind: str = "smooth") -> torch.Tensor:
     """Synthetic SEVIR-VIL-like uint8 tensor in the on-disk NHWT layout
