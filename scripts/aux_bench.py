@@ -52,6 +52,39 @@ def main():
         ms = timeit(lambda: d(x))
         out.append({"config": "5: NLayerDiscriminator forward 384x384", "batch": b, "ms": ms, "frames_per_s": b / ms * 1e3,
                     "nominal_tflops": b * 14.175e9 / (ms * 1e-3) / 1e12})
+    # ---- SURVEY 8f components: latent compressors on 48x48x4 latents, panel rendering, SEVIR device staging
+    from weatherforecastingtoolkit_b200.predictors import ConvAttnModel, ConvModel
+    from weatherforecastingtoolkit_b200 import render
+    from weatherforecastingtoolkit_b200.datastage import DeviceSEVIRLoader
+    ca = ConvAttnModel().eval()
+    cm = ConvModel().eval()
+    for b in (148, 32 * 25):
+        x = torch.randn(b, 4, 48, 48, device=dev)
+        ms = timeit(lambda: ca(x))
+        out.append({"config": "f.4: ConvAttnModel forward (one CTA per frame, fp32)", "batch": b, "ms": ms,
+                    "frames_per_s": b / ms * 1e3, "nominal_tflops": b * 0.60e9 / (ms * 1e-3) / 1e12})
+        x5 = x.unsqueeze(0)
+        ms = timeit(lambda: cm(x5))
+        out.append({"config": "f.4: ConvModel forward (one CTA per frame, fp32)", "batch": b, "ms": ms,
+                    "frames_per_s": b / ms * 1e3})
+    p = torch.rand(32, 12, 1, 384, 384, device=dev)
+    t = torch.rand(32, 12, 1, 384, 384, device=dev)
+    ms = timeit(lambda: render.render_panels(p, t))
+    px = p.numel()
+    out.append({"config": "f.3: render_panels 32x12 frames 384x384 (8 B read + 15 B written per pixel)", "ms": ms,
+                "frames_per_s": 384 / ms * 1e3, "GB_per_s": px * 23 / (ms * 1e-3) / 1e9})
+    ev = S.make_loader_events(24, 384, 384, 49, seed=3).numpy()
+    ld = DeviceSEVIRLoader(ev, batch_size=32, layout="NTCHW")
+
+    def one_pass():
+        ld.reset()
+        for _ in ld:
+            pass
+    ms = timeit(one_pass, reps=3, warm=1)
+    nseq = len(ld) * 32
+    out.append({"config": "f.2: DeviceSEVIRLoader pass, 24 events -> 72 sequences (uint8 H2D + window kernel)", "ms": ms,
+                "sequences_per_s": nseq / ms * 1e3, "h2d_MB_per_pass": 24 * 384 * 384 * 49 / 1e6,
+                "reference_fp32_h2d_MB_per_pass": nseq * 384 * 384 * 25 * 4 / 1e6})
     for r in out:
         print(json.dumps(r))
 
