@@ -351,7 +351,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="sequences per GPU (BASELINE configs[1]: 32)")
-    ap.add_argument("--frames-per-call", type=int, default=32)
+    ap.add_argument("--frames-per-call", type=int, default=37,
+                    help="frames per AutoencoderKL call; 37 makes every layer's tile count a multiple of the 74 CTA pairs")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--breakdown", default=None, help="write a per-layer conv-GEMM timing table (JSON) to this path")
     args = ap.parse_args()

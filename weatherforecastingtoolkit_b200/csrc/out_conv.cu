@@ -54,10 +54,11 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
   extern __shared__ __align__(16) uint8_t s_raw[];
   float* s_a = reinterpret_cast<float*>(s_raw);        // [C]  (already halved: silu(z) = h + h*tanh(h), h = z/2)
   float* s_b = s_a + C;                                // [C]
-  float* s_d = s_b + C;                                // [2][kTcMTiles*16][9] (double-buffered per tile)
-  uint2* s_bf = reinterpret_cast<uint2*>(s_d + 2 * kTcMTiles * 16 * 9);   // [KSTEPS][2][32] weight fragments
+  float* s_d = s_b + C;                                // [kTcMTiles*16][9]
+  uint2* s_bf = reinterpret_cast<uint2*>(s_d + kTcMTiles * 16 * 9);       // [KSTEPS][2][32] weight fragments
   __half* s_t = reinterpret_cast<__half*>(s_bf + KSTEPS * 2 * 32);    // [kTcWarps][16][kPitch]
   __shared__ float s_mean[64], s_rstd[64];
+  __shared__ int s_pixoff[kTcMTiles * 16];   // halo pixel q -> element offset of its channel 0 relative to the tile origin
   const int n = blockIdx.z;
   const int y0 = blockIdx.y * kOT;
   const int cpg = C / groups;
@@ -78,6 +79,10 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
     const float a = s_rstd[ch / cpg] * gamma[ch];
     s_a[ch] = 0.5f * a;
     s_b[ch] = 0.5f * (beta[ch] - s_mean[ch / cpg] * a);
+  }
+  for (int q = threadIdx.x; q < kTcMTiles * 16; q += blockDim.x) {
+    const int qq = min(q, kOH * kOH - 1);   // rows past the halo square re-read its last pixel (their d values are unused)
+    s_pixoff[q] = ((qq / kOH - 1) * w + (qq % kOH - 1)) * C;
   }
   // weight fragments (B operand, "col" layout) staged once per block in shared memory as [ks][nt][lane] uint2:
   // b0 = {W[k][n], W[k+1][n]}, k = ks*16 + (lane%4)*2, n = nt*8 + lane/4; b1 the same 8 channels further.
@@ -122,6 +127,16 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
   auto issue_loads = [&](const int item, uint4 (&u)[kIters], uint32_t& okmask) {
     const int ts = item / kPerTile, mt = warp + kTcWarps * (item - ts * kPerTile);
     const int x0 = (tx_first + ts) * kOT;
+    if (y0 >= 1 && y0 + kOT < h && x0 >= 1 && x0 + kOT < w) {
+      // interior tile: every halo pixel is inside the image; the address is the tile origin plus a per-pixel table
+      // entry (the general path below spends ~20 integer instructions per 16-byte load on coordinates and clamps)
+      const __half* origin = x + ((static_cast<int64_t>(n) * h + y0) * w + x0) * C + (lane % kChunks) * 8;
+      okmask = (1u << kIters) - 1u;
+#pragma unroll
+      for (int it = 0; it < kIters; ++it)
+        u[it] = __ldg(reinterpret_cast<const uint4*>(origin + s_pixoff[mt * 16 + (it * 32 + lane) / kChunks]));
+      return;
+    }
     okmask = 0;
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
@@ -180,8 +195,8 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
         if (tap < 9) sd[(mt * 16 + row) * 9 + tap] = acc[nt][j];
       }
   };
-  // after a tile's m-tiles: block barrier, then the 9-tap gather from that tile's s_d buffer (double-buffered, so the
-  // next tile's m-tiles may already be written while stragglers still gather)
+  // after a tile's m-tiles: block barrier, the 9-tap gather from s_d, and a second barrier before the next tile's
+  // m-tiles overwrite it (a second s_d buffer cost a resident block per SM and bought nothing)
   auto finish_tile = [&](const int ts, const float* sd) {
     __syncthreads();
     const int x0 = (tx_first + ts) * kOT;
@@ -197,6 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
         out[(static_cast<int64_t>(n) * h + y) * w + xx] = acc;
       }
     }
+    __syncthreads();
   };
   // single register buffer: with <= 72 registers four blocks (28 warps) fit an SM and thread-level parallelism hides the
   // load latency better than a register double buffer at two blocks per SM did
@@ -205,8 +221,8 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
   for (int item = 0; item < n_items; ++item) {
     const int ts = item / kPerTile;
     issue_loads(item, u0, ok0);
-    process(item, u0, ok0, s_d + (ts & 1) * (kTcMTiles * 16 * 9));
-    if (item % kPerTile == kPerTile - 1) finish_tile(ts, s_d + (ts & 1) * (kTcMTiles * 16 * 9));
+    process(item, u0, ok0, s_d);
+    if (item % kPerTile == kPerTile - 1) finish_tile(ts, s_d);
   }
 }
 
@@ -214,7 +230,7 @@ template <int KSTEPS>
 int launch_tail_tc(const __half* x, const double* stats, const float* gamma, const float* beta, int n, int h, int w,
                    int groups, float eps, const float* weight, float bias, float* out, cudaStream_t s) {
   constexpr int C = KSTEPS * 16;
-  const size_t smem = (2 * C + 2 * kTcMTiles * 16 * 9) * sizeof(float) + static_cast<size_t>(KSTEPS) * 2 * 32 * 8 +
+  const size_t smem = (2 * C + kTcMTiles * 16 * 9) * sizeof(float) + static_cast<size_t>(KSTEPS) * 2 * 32 * 8 +
                       static_cast<size_t>(kTcWarps) * 16 * (C + 8) * 2;
   static bool attr_set = false;
   if (!attr_set) {
