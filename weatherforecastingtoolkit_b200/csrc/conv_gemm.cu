@@ -580,6 +580,8 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       const TileCoord t = decode_tile(p, tile);
       const int x0 = (t.tx * kBlocksPerTile + static_cast<int>(cta_rank) * MB) * 8 - 1;
       const int y0 = t.ty * 16 - 1;
+      // frame of this CTA's next tile: its (scale, shift) rows are prefetched into L1 during this tile's last K block
+      const int next_frame = (tile + tile_step < total_tiles) ? decode_tile(p, tile + tile_step).frame : -1;
       // all K blocks of source 0 (every tap), then those of source 1 (fused 1x1 shortcut, centre tap)
       auto step = [&](const int seg, const int kb) {
         
@@ -630,6 +632,16 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
               gb[2 * j] = 0.5f * v.y;
               ga[2 * j + 1] = 0.5f * v.z;
               gb[2 * j + 1] = 0.5f * v.w;
+            }
+            // The 64 bytes above come from L2 and are consumed at once: every K block began with a full L2 round trip
+            // (16 % of the transform warps' samples in the 128-wide kernel). Pull the NEXT K block's rows into L1 now.
+            {
+              const bool more = kb + 1 < p.seg_kblocks[0];
+              const int nf = more ? t.frame : next_frame;
+              if (nf >= 0 && (lc & 1) == 0) {
+                const float2* np = p.gn_table + static_cast<int64_t>(nf) * p.gn_cin + (more ? kb + 1 : 0) * kBlockK + lc * 8;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+              }
             }
             }
             // Software-pipelined: each thread owns rows (xt>>3) + 16*i of the box; the loads of kXfGroup rows are
