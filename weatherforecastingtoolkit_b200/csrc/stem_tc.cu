@@ -28,7 +28,7 @@ __device__ __forceinline__ void stem_mma_16816(float (&c)[4], const uint32_t (&a
 // in [n, cin, h, w] fp32; wt [KSTEPS*16][cout] fp16 with row k = ci*9 + tap (ci = cin is the constant-one plane when
 // `ones_plane`), zero rows beyond K; out [n, h, w, cout] fp16; stats [n][cout/cpg][2] double.
 template <int KSTEPS>
-__global__ void __launch_bounds__(kStemTcThreads, 5) conv3x3_stem_tc_kernel(
+__global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_stem_tc_kernel(
     const float* __restrict__ in, int cin, int ones_plane, int h, int w, const __half* __restrict__ wt,
     const float* __restrict__ bias, int cout, __half* __restrict__ out, double* __restrict__ stats, int cpg,
     int tiles_per_warp) {
