@@ -162,11 +162,19 @@ class PathBNowcast(nn.Module):
     """``Model`` of the reference experiment, inference side (train.py:58-125)."""
 
     def __init__(self, autoencoder_cfg: dict, input_frames: int = INPUT_FRAMES, pred_frames: int = PRED_FRAMES,
-                 posterior: str = "mode", frames_per_call: int = 37):
+                 posterior: str = "mode", frames_per_call: int = 37, predictor: Optional[nn.Module] = None):
+        """``predictor``: any module with ``rollout(latents[B, t_in + t_out, C, h, w]) -> (pred, tgt, val_loss)`` --
+        the default ``nn.Linear(13*4, 12*4)`` of ``pretrained_ae_linear_sevir`` or ``predictors.DLinear`` /
+        ``predictors.DLinearIndcIndp`` of the ``pretrained_ae_dlinear_*`` experiments (same ``validation_step`` around
+        ``self.predictor``, pretrained_ae_dlinear_sevir/train.py:179-192)."""
         super().__init__()
         self.autoencoder = Autoencoder(autoencoder_cfg, posterior=posterior, frames_per_call=frames_per_call)
         self.input_frames, self.pred_frames = input_frames, pred_frames
-        self.predictor = LatentLinearPredictor(input_frames, pred_frames, autoencoder_cfg.get("latent_channels", 4))
+        if predictor is None:
+            predictor = LatentLinearPredictor(input_frames, pred_frames, autoencoder_cfg.get("latent_channels", 4))
+        elif not hasattr(predictor, "rollout"):
+            raise TypeError("predictor must provide rollout(latents) -> (pred, tgt, val_loss)")
+        self.predictor = predictor
 
     def forward(self, x):
         return self.predictor(x)
@@ -191,6 +199,48 @@ class PathBNowcast(nn.Module):
         over the ranks of ``process_group`` with one all-reduce."""
         dp, dt, loss = self.validation_step(batch)
         res = wf_metrics.calc_metrics(dp, dt, extended=extended, process_group=process_group)
+        res["val_loss"] = float(loss.item())
+        return res
+
+
+class LatentReconstruction(nn.Module):
+    """``Model`` of the latent-compressor experiments, inference side: ``pretrained_ae_convae_sevir/train.py:145-198``
+    (``predictors.ConvModel``, all frames of a sequence) and ``pretrained_ae_convattn_ae_sevir/train.py:167-222``
+    (``predictors.ConvAttnModel``, one frame per sample). ``validation_step``: encode with the frozen AutoencoderKL,
+    run the compressor on the latents, ``nn.HuberLoss()(pred, latents)``, decode the reconstruction; the caller scores
+    it against the INPUT frames (``log_metrics(decoded_pred, inp, ...)``)."""
+
+    def __init__(self, autoencoder_cfg: dict, predictor: nn.Module, posterior: str = "mode", frames_per_call: int = 37):
+        super().__init__()
+        self.autoencoder = Autoencoder(autoencoder_cfg, posterior=posterior, frames_per_call=frames_per_call)
+        self.predictor = predictor
+
+    @torch.no_grad()
+    def forward(self, latents: torch.Tensor, return_loss: bool = False):
+        """latents [B, T, C, 48, 48] -> reconstruction of the same shape (``Model.forward`` of both scripts)."""
+        b, t = latents.shape[:2]
+        from .predictors import ConvAttnModel
+        if isinstance(self.predictor, ConvAttnModel):
+            assert t == 1, "input should be 1 frame"       # pretrained_ae_convattn_ae_sevir/train.py:179
+            out = self.predictor(latents[:, 0], return_loss=return_loss)
+            rec = out[1].unsqueeze(1)
+        else:
+            out = self.predictor(latents, return_loss=return_loss)
+            rec = out[1]
+        return (rec, out[2]) if return_loss else rec
+
+    @torch.no_grad()
+    def validation_step(self, batch: torch.Tensor):
+        """batch [B, H, W, T] uint8 or float in [0, 1] -> (decoded_pred, inp [B, T, 1, H, W], val_loss)."""
+        inp = stage_vil(batch) if batch.dtype == torch.uint8 else batch.permute(0, 3, 1, 2).unsqueeze(2).contiguous()
+        lat = self.autoencoder.encode(inp)
+        rec, loss = self.forward(lat, return_loss=True)
+        return self.autoencoder.decode(rec), inp, loss
+
+    @torch.no_grad()
+    def evaluate(self, batch: torch.Tensor, process_group=None, extended: bool = False) -> Dict[str, float]:
+        dp, inp, loss = self.validation_step(batch)
+        res = wf_metrics.calc_metrics(dp, inp, extended=extended, process_group=process_group)
         res["val_loss"] = float(loss.item())
         return res
 
