@@ -315,12 +315,12 @@ def run_b200_arm(args):
                 # `achieved` aggregates ~4800 launches of different layer shapes; `traffic` is the DRAM bytes of ONE launch of
                 # the dominant variant (conv_gemm<256> HALO pair kernel, 256->256 @192^2, 8 frames) from its `ncu --set
                 # full` capture; the second capture covers the other large variant
-                "traffic": 258.6e6,
-                "traffic_ncu": {"conv_gemm<256> gn 256->256 @192^2 x 8 frames": {"dram_bytes": 258.6e6, "algorithmic_bytes": 302.0e6,
-                                                                              "tensor_pipe_active_pct": 92.2},
-                                "conv_gemm<128> gn 128->128 @384^2 x 8 frames": {"dram_bytes": 551.7e6, "algorithmic_bytes": 604.0e6,
-                                                                               "tensor_pipe_active_pct": 71.2},
-                                "source": "profiles/r1_prof_final3_n256_raw.csv, r1_prof_final3_n128_raw.csv"},
+                "traffic": 258.4e6,
+                "traffic_ncu": {"conv_gemm<256> gn 256->256 @192^2 x 8 frames": {"dram_bytes": 258.4e6, "algorithmic_bytes": 302.0e6,
+                                                                              "tensor_pipe_active_pct": 91.9},
+                                "conv_gemm<128> gn 128->128 @384^2 x 8 frames": {"dram_bytes": 553.1e6, "algorithmic_bytes": 604.0e6,
+                                                                               "tensor_pipe_active_pct": 70.5},
+                                "source": "profiles/r1_prof_final4_n256_raw.csv, r1_prof_final4_n128_raw.csv"},
                 "peak_source": peaks["which"],
                 "launches_timed": tsum["launches"], "kernel_ms_per_step": tsum["ms"] / args.steps,
                 "kernel_share_of_step": tsum["ms"] / ms if ms > 0 else None,
