@@ -340,8 +340,10 @@ int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, v
  *      recon [n, cin, 48, 48]; huber_sums (optional, double[2]) += (sum of HuberLoss(recon, x) terms, element count)
  *      as in the experiment's validation_step (train.py:206-209).  mode 0: encode + decode (forward), 1: encode only
  *      (z written), 2: decode only (z read; x may be NULL).  Fixed by the kernel: 48 x 48 input, embed 128, 8 heads,
- *      feed-forward 512; runtime: cin <= 8, layers <= 8, latent_dim <= 512.  weights: 28 + 30 * layers DEVICE fp32
- *      pointers, 16-byte aligned, in the order listed in predictors.py (ConvAttnModel._weight_pointers). */
+ *      feed-forward 512; runtime: cin <= 8, layers <= 8, latent_dim <= 512.  weights: 29 + 30 * layers DEVICE fp32
+ *      pointers, 16-byte aligned, in the order listed in predictors.py (ConvAttnModel._weight_pointers); the matrices
+ *      of the token GEMMs (self-attention in/out projections, linear1, linear2, the pooling key/value projection) are
+ *      passed TRANSPOSED ([in, out]), everything else in the PyTorch layout. */
 int wfk_convattn_forward(const float* x, int n, int cin, int layers, int latent_dim, const float* const* weights,
                          int num_weights, float* z, float* recon, double* huber_sums, int mode, void* stream);
 

@@ -48,7 +48,7 @@ def test_convattn_oracle_vs_reference_class(case):
     torch.testing.assert_close(rec, rec2, rtol=0, atol=5e-5)
     mine = Mine()
     assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == {k: tuple(v.shape) for k, v in m.state_dict().items()}
-    assert len(mine._weight_pointers()) == 28 + 30 * 4 == len(list(mine.parameters()))
+    assert len(mine._weight_pointers()) == 29 + 30 * 4 == len(list(mine.parameters())) + 1   # pool in_proj twice
 
 
 def test_convattn_host_errors(case):

@@ -30,12 +30,14 @@ constexpr int kCaRowsPerThread = 9;   // 16 row groups x 9 rows = 144
 constexpr int kCaMaxLayers = 8;
 constexpr int kCaMaxLatent = 512;
 
+// Matrices consumed by ca_gemm are stored TRANSPOSED ([in, out], packed once on the host) so that a warp's weight loads
+// at one k are 512 contiguous bytes; matrices consumed by ca_linear keep the PyTorch [out, in] layout.
 struct CaAttnW {
-  const float *in_w, *in_b, *out_w, *out_b;  // in_proj [384, 128] (q | k | v rows), out_proj [128, 128]
+  const float *in_w, *in_b, *out_w, *out_b;  // in_proj (q | k | v along the output dimension), out_proj
 };
 struct CaEncLayerW {
   CaAttnW sa;
-  const float *l1_w, *l1_b, *l2_w, *l2_b;  // linear1 [512, 128], linear2 [128, 512]
+  const float *l1_w, *l1_b, *l2_w, *l2_b;  // linear1^T [128, 512], linear2^T [512, 128]
   const float *n1_w, *n1_b, *n2_w, *n2_b;
 };
 struct CaDecLayerW {
@@ -48,7 +50,8 @@ struct ConvAttnWeights {
   const float* enc_pos;  // [144, 128]
   CaEncLayerW enc[kCaMaxLayers];
   const float* pool_q;  // [128]
-  CaAttnW pool;
+  CaAttnW pool;            // [out, in] (the query / output projections are matrix-vector products)
+  const float* pool_in_wt; // in_proj^T [128, 384] for the key / value GEMMs
   const float *eh_ln_w, *eh_ln_b, *eh_w, *eh_b;  // encoder_head: LayerNorm(128), Linear [latent, 128]
   const float *dh_w, *dh_b;                      // decoder_head [128, latent]
   const float *dec_q, *dec_pos;                  // [144, 128] each
@@ -89,12 +92,15 @@ __device__ void ca_row_stats(const float* x, float* mu, float* rs) {
 
 enum { CA_STORE = 0, CA_STORE_GELU = 1, CA_ACC = 2 };
 
-// out[144, n] (op)= f(in[144, 128]) W^T + bias.  `wrow(c)` is the 128-long weight row of output column c, `bcol(c)` its
-// bias; with LN the input rows are normalised on the fly ((x - mu) * rs * g + b: the reference's rounding order).
-// Thread (row group of 9, 4 consecutive columns): x reads are warp broadcasts, weight reads 128-bit and L1/L2-resident.
-template <bool LN, int MODE, typename WRow, typename BCol>
+// out[144, n] (op)= f(in[144, 128]) W^T + bias with W^T given k-major: wt[k * ldw + col(c)] is the weight of input k for
+// output column c (`col` maps 4-aligned groups of output columns to 4 consecutive matrix columns), `bcol(c)` its bias;
+// with LN the input rows are normalised on the fly ((x - mu) * rs * g + b: the reference's rounding order).
+// Thread (row group of 9, 4 consecutive columns): x reads are warp broadcasts, the warp's weight read at one k is one
+// contiguous 512-byte row segment (L1/L2-resident).
+template <bool LN, int MODE, typename Col, typename BCol>
 __device__ void ca_gemm(const float* in, const float* mu, const float* rs, const float* __restrict__ g,
-                        const float* __restrict__ b, WRow wrow, BCol bcol, int n, float* out) {
+                        const float* __restrict__ b, const float* __restrict__ wt, int ldw, Col col, BCol bcol, int n,
+                        float* out) {
   const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int c0 = cg * 4, r0 = rg * kCaRowsPerThread;
   if (c0 < n) {
@@ -103,10 +109,7 @@ __device__ void ca_gemm(const float* in, const float* mu, const float* rs, const
     for (int r = 0; r < kCaRowsPerThread; ++r)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
-    const float* w0 = wrow(c0);
-    const float* w1 = wrow(c0 + 1);
-    const float* w2 = wrow(c0 + 2);
-    const float* w3 = wrow(c0 + 3);
+    const float* wp = wt + col(c0);
     float m[kCaRowsPerThread], s[kCaRowsPerThread];
     if (LN) {
 #pragma unroll
@@ -114,10 +117,10 @@ __device__ void ca_gemm(const float* in, const float* mu, const float* rs, const
     }
 #pragma unroll 2
     for (int k = 0; k < kCaD; k += 4) {
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(w0 + k));
-      const float4 a1 = __ldg(reinterpret_cast<const float4*>(w1 + k));
-      const float4 a2 = __ldg(reinterpret_cast<const float4*>(w2 + k));
-      const float4 a3 = __ldg(reinterpret_cast<const float4*>(w3 + k));
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(wp + (k + 0) * ldw));  // input k:     columns c0 .. c0+3
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(wp + (k + 1) * ldw));
+      const float4 a2 = __ldg(reinterpret_cast<const float4*>(wp + (k + 2) * ldw));
+      const float4 a3 = __ldg(reinterpret_cast<const float4*>(wp + (k + 3) * ldw));
       float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (LN) {
         g4 = __ldg(reinterpret_cast<const float4*>(g + k));
@@ -132,10 +135,10 @@ __device__ void ca_gemm(const float* in, const float* mu, const float* rs, const
           x.z = (x.z - m[r]) * s[r] * g4.z + b4.z;
           x.w = (x.w - m[r]) * s[r] * g4.w + b4.w;
         }
-        acc[r][0] = fmaf(x.x, a0.x, fmaf(x.y, a0.y, fmaf(x.z, a0.z, fmaf(x.w, a0.w, acc[r][0]))));
-        acc[r][1] = fmaf(x.x, a1.x, fmaf(x.y, a1.y, fmaf(x.z, a1.z, fmaf(x.w, a1.w, acc[r][1]))));
-        acc[r][2] = fmaf(x.x, a2.x, fmaf(x.y, a2.y, fmaf(x.z, a2.z, fmaf(x.w, a2.w, acc[r][2]))));
-        acc[r][3] = fmaf(x.x, a3.x, fmaf(x.y, a3.y, fmaf(x.z, a3.z, fmaf(x.w, a3.w, acc[r][3]))));
+        acc[r][0] = fmaf(x.x, a0.x, fmaf(x.y, a1.x, fmaf(x.z, a2.x, fmaf(x.w, a3.x, acc[r][0]))));
+        acc[r][1] = fmaf(x.x, a0.y, fmaf(x.y, a1.y, fmaf(x.z, a2.y, fmaf(x.w, a3.y, acc[r][1]))));
+        acc[r][2] = fmaf(x.x, a0.z, fmaf(x.y, a1.z, fmaf(x.z, a2.z, fmaf(x.w, a3.z, acc[r][2]))));
+        acc[r][3] = fmaf(x.x, a0.w, fmaf(x.y, a1.w, fmaf(x.z, a2.w, fmaf(x.w, a3.w, acc[r][3]))));
       }
     }
     const float bias[4] = {bcol(c0), bcol(c0 + 1), bcol(c0 + 2), bcol(c0 + 3)};
@@ -177,9 +180,8 @@ __device__ void ca_self_attention(float* x, float* qkv, float* o, const CaShared
     const float* in_w = W.in_w;
     const float* in_b = W.in_b;
     auto row = [=](int c) { return (c >> 5) * kCaD + pass * 32 + (c & 31); };  // q / k / v block, pair offset, channel
-    ca_gemm<true, CA_STORE>(
-        x, S.mu, S.rs, ln_w, ln_b, [=](int c) { return in_w + row(c) * kCaD; }, [=](int c) { return __ldg(in_b + row(c)); },
-        96, qkv);
+    ca_gemm<true, CA_STORE>(x, S.mu, S.rs, ln_w, ln_b, in_w, 3 * kCaD, row, [=](int c) { return __ldg(in_b + row(c)); }, 96,
+                            qkv);
     if (threadIdx.x < 2 * kCaT) {
       const int h = threadIdx.x / kCaT, i = threadIdx.x - h * kCaT;
       float q[kCaDh], acc[kCaDh];
@@ -209,9 +211,8 @@ __device__ void ca_self_attention(float* x, float* qkv, float* o, const CaShared
   }
   const float* ow = W.out_w;
   const float* ob = W.out_b;
-  ca_gemm<false, CA_ACC>(
-      o, nullptr, nullptr, nullptr, nullptr, [=](int c) { return ow + c * kCaD; }, [=](int c) { return __ldg(ob + c); }, kCaD,
-      x);
+  ca_gemm<false, CA_ACC>(o, nullptr, nullptr, nullptr, nullptr, ow, kCaD, [](int c) { return c; },
+                         [=](int c) { return __ldg(ob + c); }, kCaD, x);
 }
 
 // Feed-forward block of a pre-norm layer: x += linear2(GELU(linear1(LN(x)))), hidden units in four chunks of 128.
@@ -221,14 +222,15 @@ __device__ void ca_feed_forward(float* x, float* hid, float* sum, const CaShared
                                 const float* __restrict__ ln_b) {
   ca_row_stats(x, S.mu, S.rs);
   for (int ch = 0; ch < kCaFf / kCaD; ++ch) {
-    ca_gemm<true, CA_STORE_GELU>(
-        x, S.mu, S.rs, ln_w, ln_b, [=](int c) { return l1_w + (ch * kCaD + c) * kCaD; },
-        [=](int c) { return __ldg(l1_b + ch * kCaD + c); }, kCaD, hid);
-    auto w2 = [=](int c) { return l2_w + c * kCaFf + ch * kCaD; };
+    ca_gemm<true, CA_STORE_GELU>(x, S.mu, S.rs, ln_w, ln_b, l1_w, kCaFf, [=](int c) { return ch * kCaD + c; },
+                                 [=](int c) { return __ldg(l1_b + ch * kCaD + c); }, kCaD, hid);
+    const float* w2 = l2_w + ch * kCaD * kCaD;   // rows ch*128 .. of linear2^T [512, 128]
+    auto ident = [](int c) { return c; };
     if (ch == 0)
-      ca_gemm<false, CA_STORE>(hid, nullptr, nullptr, nullptr, nullptr, w2, [=](int c) { return __ldg(l2_b + c); }, kCaD, sum);
+      ca_gemm<false, CA_STORE>(hid, nullptr, nullptr, nullptr, nullptr, w2, kCaD, ident, [=](int c) { return __ldg(l2_b + c); },
+                               kCaD, sum);
     else
-      ca_gemm<false, CA_ACC>(hid, nullptr, nullptr, nullptr, nullptr, w2, [](int) { return 0.f; }, kCaD, sum);
+      ca_gemm<false, CA_ACC>(hid, nullptr, nullptr, nullptr, nullptr, w2, kCaD, ident, [](int) { return 0.f; }, kCaD, sum);
   }
   for (int e = threadIdx.x; e < kCaT * (kCaD / 4); e += kCaThreads) {
     const int r = e >> 5, c = (e & 31) * 4;
@@ -369,12 +371,10 @@ __global__ void __launch_bounds__(kCaThreads, 1) convattn_kernel(const float* __
       const float* in_w = W.pool.in_w;
       const float* in_b = W.pool.in_b;
       ca_linear(W.pool_q, kCaD, in_w, in_b, kCaD, S.vec[0]);  // q = Wq pooling_query + bq (global input is fine here)
-      ca_gemm<false, CA_STORE>(
-          X, nullptr, nullptr, nullptr, nullptr, [=](int c) { return in_w + (kCaD + c) * kCaD; },
-          [=](int c) { return __ldg(in_b + kCaD + c); }, kCaD, A);
-      ca_gemm<false, CA_STORE>(
-          X, nullptr, nullptr, nullptr, nullptr, [=](int c) { return in_w + (2 * kCaD + c) * kCaD; },
-          [=](int c) { return __ldg(in_b + 2 * kCaD + c); }, kCaD, B);
+      ca_gemm<false, CA_STORE>(X, nullptr, nullptr, nullptr, nullptr, W.pool_in_wt, 3 * kCaD, [](int c) { return kCaD + c; },
+                               [=](int c) { return __ldg(in_b + kCaD + c); }, kCaD, A);
+      ca_gemm<false, CA_STORE>(X, nullptr, nullptr, nullptr, nullptr, W.pool_in_wt, 3 * kCaD,
+                               [](int c) { return 2 * kCaD + c; }, [=](int c) { return __ldg(in_b + 2 * kCaD + c); }, kCaD, B);
       float* sc = X;  // [8, 144]
       for (int e = threadIdx.x; e < 8 * kCaT; e += kCaThreads) {
         const int h = e / kCaT, j = e - h * kCaT;
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(kCaThreads, 1) convattn_kernel(const float* __
 
 }  // namespace wfk
 
-// weights: 28 + 30 L pointers (L = layers) in the order of the reference module (see
+// weights: 29 + 30 L pointers (L = layers) in the order of the reference module (see
 // weatherforecastingtoolkit_b200/predictors.py::ConvAttnModel._weight_pointers).
 extern "C" int wfk_convattn_forward(const float* x, int n, int cin, int layers, int latent_dim, const float* const* weights,
                                     int num_weights, float* z, float* recon, double* huber_sums, int mode, void* stream) {
@@ -486,7 +486,7 @@ extern "C" int wfk_convattn_forward(const float* x, int n, int cin, int layers, 
   WFK_REQUIRE(n > 0 && cin >= 1 && cin <= 8, "bad shape n=%d cin=%d", n, cin);
   WFK_REQUIRE(layers >= 1 && layers <= wfk::kCaMaxLayers, "1..%d transformer layers supported", wfk::kCaMaxLayers);
   WFK_REQUIRE(latent_dim >= 4 && latent_dim <= wfk::kCaMaxLatent, "latent_dim must be in 4..%d", wfk::kCaMaxLatent);
-  const int expect = 28 + 30 * layers;
+  const int expect = 29 + 30 * layers;
   WFK_REQUIRE(num_weights == expect, "expected %d weight pointers for %d layers, got %d", expect, layers, num_weights);
   for (int i = 0; i < num_weights; ++i) {
     WFK_REQUIRE(weights[i] != nullptr, "weights[%d] is NULL", i);
@@ -507,6 +507,7 @@ extern "C" int wfk_convattn_forward(const float* x, int n, int cin, int layers, 
   }
   W.pool_q = next();
   attn(W.pool);
+  W.pool_in_wt = next();
   W.eh_ln_w = next(), W.eh_ln_b = next(), W.eh_w = next(), W.eh_b = next();
   W.dh_w = next(), W.dh_b = next();
   W.dec_q = next(), W.dec_pos = next();

@@ -287,29 +287,41 @@ class ConvAttnModel(nn.Module):
             nn.init.zeros_(m.bias)
 
     def _weight_pointers(self):
-        """Parameters in the order ``wfk_convattn_forward`` reads them (28 + 30 * layers tensors)."""
-        def attn(a):
-            return [a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias]
+        """Tensors in the order ``wfk_convattn_forward`` reads them (29 + 30 * layers). Entries wrapped in ``_T`` are the
+        matrices of the token GEMMs: the kernel wants them transposed ([in, out]) so a warp reads contiguous rows."""
+        class _T:  # marker: pass this parameter transposed
+            def __init__(self, p):
+                self.p = p
+
+        def attn(a, transposed):
+            w = (lambda p: _T(p)) if transposed else (lambda p: p)
+            return [w(a.in_proj_weight), a.in_proj_bias, w(a.out_proj.weight), a.out_proj.bias]
 
         def wb(*mods):
             return [p for m in mods for p in (m.weight, m.bias)]
+
+        def ff(l):
+            return [_T(l.linear1.weight), l.linear1.bias, _T(l.linear2.weight), l.linear2.bias]
         ec, dc = self.encoder_cnn, self.decoder_cnn
         out = wb(ec[0], ec[1], ec[3], ec[4]) + [self.encoder_pos_embedding]
         for l in self.encoder_tf.layers:
-            out += attn(l.self_attn) + wb(l.linear1, l.linear2, l.norm1, l.norm2)
-        out += [self.pooling_query] + attn(self.attention_pool) + wb(self.encoder_head[0], self.encoder_head[1])
+            out += attn(l.self_attn, True) + ff(l) + wb(l.norm1, l.norm2)
+        out += [self.pooling_query] + attn(self.attention_pool, False) + [_T(self.attention_pool.in_proj_weight)]
+        out += wb(self.encoder_head[0], self.encoder_head[1])
         out += wb(self.decoder_head) + [self.decoder_queries, self.decoder_pos_embedding]
         for l in self.decoder_tf.layers:
-            out += attn(l.self_attn) + attn(l.multihead_attn) + wb(l.linear1, l.linear2, l.norm1, l.norm2, l.norm3)
-        return out + wb(dc[0], dc[1], dc[3])
+            out += attn(l.self_attn, True) + attn(l.multihead_attn, False) + ff(l) + wb(l.norm1, l.norm2, l.norm3)
+        out += wb(dc[0], dc[1], dc[3])
+        return [(e.p, True) if isinstance(e, _T) else (e, False) for e in out]
 
     def _pack(self, device):
         params = self._weight_pointers()
-        key = (str(device), sum(p._version for p in params), tuple(p.data_ptr() for p in params))
+        key = (str(device), sum(p._version for p, _ in params), tuple(p.data_ptr() for p, _ in params))
         if self._packed is not None and self._packed[0] == key:
             return self._packed[1]
         import ctypes as C
-        tensors = [p.detach().to(device=device, dtype=torch.float32).contiguous() for p in params]
+        tensors = [(p.detach().t() if tr else p.detach()).to(device=device, dtype=torch.float32).contiguous()
+                   for p, tr in params]
         arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         self._packed = (key, (tensors, arr))
         return self._packed[1]
