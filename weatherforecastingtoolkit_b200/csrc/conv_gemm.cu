@@ -1512,7 +1512,14 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   if (plan->pair) {
     const long pairs = plan->halo ? (plan->bn == 256 ? wfk::max_active_pairs<256, true>() : wfk::max_active_pairs<128, true>())
                                   : (plan->bn == 256 ? wfk::max_active_pairs<256, false>() : wfk::max_active_pairs<128, false>());
-    plan->grid = static_cast<int>(2 * (total_tiles < pairs ? total_tiles : pairs));
+    long use = pairs;
+    // experiment knob: run on fewer CTA pairs (what a 4-CTA-cluster design would get: 66 of 74) to see how much of the
+    // lost SMs the power cap gives back as clock
+    if (const char* e = std::getenv("WFK_MAX_PAIRS")) {
+      const long cap = std::atol(e);
+      if (cap >= 1 && cap < use) use = cap;
+    }
+    plan->grid = static_cast<int>(2 * (total_tiles < use ? total_tiles : use));
   } else {
     plan->grid = static_cast<int>(total_tiles < wfk::g_num_sms ? total_tiles : wfk::g_num_sms);
   }
