@@ -91,3 +91,40 @@ def test_latent_reconstruction_step(akl_weights, kind):
     assert loss.item() == pytest.approx(wl.item(), rel=2e-2)
     res = net.evaluate(u8.to(DEV), extended=True)
     assert res["val_loss"] == pytest.approx(loss.item(), rel=1e-6) and 0.0 <= res["SSIM"] <= 1.0
+
+
+@pytest.mark.gpu
+def test_validation_epoch_end_to_end(akl_weights):
+    """Loader -> rollout -> accumulator -> panels (scripts/validate_epoch.py) on small synthetic events: the epoch scores
+    equal calc_metrics of the concatenated batches; the loader's float batches equal the reference formula."""
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "scripts"))
+    import validate_epoch as V
+    from weatherforecastingtoolkit_b200 import metrics as M
+    from weatherforecastingtoolkit_b200.datastage import DeviceSEVIRLoader
+    from weatherforecastingtoolkit_b200.rollout import PathBNowcast
+    from weatherforecastingtoolkit_b200.synthetic import make_predictor_params, make_vil_sequences
+    cfg, sd = akl_weights
+    net = PathBNowcast(cfg, posterior="mode", frames_per_call=16)
+    net.autoencoder.autoencoder.load_state_dict(sd, strict=True)
+    w, b = make_predictor_params(seed=0)
+    net.predictor.weight.data.copy_(w)
+    net.predictor.bias.data.copy_(b)
+    net = net.to(DEV)
+    events = make_vil_sequences(4, 64, 64, 49, seed=9).numpy()
+    scores, mosaics, loader = V.run_epoch(events, net, batch_size=5, panels=2)
+    assert len(loader) == 2 and loader.h2d_bytes <= 2 * 3 * events[0].size       # 12 windows // 5; <= 3 events per batch
+    assert len(mosaics) == 2 and mosaics[0].shape == (3 * 64, 12 * 64, 4)
+    # the same epoch by hand: windows of the sequential sampler, one concatenated calc_metrics
+    ld = DeviceSEVIRLoader(events, batch_size=5, layout="NHWT", split_mode="floor")
+    dps, dts = [], []
+    for batch in ld:
+        x = batch["vil"]
+        assert x.shape == (5, 64, 64, 25) and float(x.max()) <= 1.0
+        dp, dt, _ = net.validation_step(x)
+        dps.append(dp), dts.append(dt)
+    want = M.calc_metrics(torch.cat(dps), torch.cat(dts), extended=True)
+    for k, v in want.items():
+        if np.isnan(v):          # a frame of the 64x64 synthetic data with a constant target has no PSNR
+            assert np.isnan(scores[k]), k
+        else:
+            assert scores[k] == pytest.approx(v, rel=1e-6, abs=1e-7), k
