@@ -45,6 +45,52 @@ def _peaks():
     return {"tflops": 1400.0, "hbm": 6650.0, "which": "fallback (B200_PROFILING.md)"}
 
 
+def bench_config(args, world):
+    """The `config` object of BOTH arms (the driver compares them): the workload and how it is cut."""
+    return {"workload": WORKLOAD, "batch_per_gpu": args.batch, "frames_per_call": args.frames_per_call,
+            "posterior": "mode", "l2": "inputs (118 MB uint8 + GB-scale activations) larger than the 126 MB L2",
+            "parallelism": f"dp{world} (sequence shards, one all-reduce of the 864-byte partials)"}
+
+
+def read_ncu_raw(path):
+    """Rows of an `ncu --page raw --csv` export as dicts {metric: float | str} (the unit row is dropped; Mbyte /
+    Kbyte / Gbyte and ms / us / ns are normalised to bytes and microseconds)."""
+    import csv
+    with open(path, newline="") as f:
+        rows = list(csv.reader(f))
+    if len(rows) < 3:
+        return []
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+             "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3, "second": 1e6}
+    out = []
+    for r in rows[2:]:
+        d = {}
+        for h, u, v in zip(hdr, units, r):
+            try:
+                d[h] = float(v.replace(",", "")) * scale.get(u, 1.0)
+            except ValueError:
+                d[h] = v
+        out.append(d)
+    return out
+
+
+def ncu_traffic(patterns):
+    """DRAM bytes of ONE launch of the dominant kernel, read from the newest committed `ncu --set full` raw export
+    under profiles/ whose name matches one of `patterns` (never typed in by hand)."""
+    import glob
+    for pat in patterns:
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", pat)), reverse=True):
+            rows = [r for r in read_ncu_raw(path) if "dram__bytes_read.sum" in r]
+            if rows:
+                r = rows[0]
+                return {"source": os.path.relpath(path, ROOT), "kernel": r.get("Kernel Name"),
+                        "dram_bytes": r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"],
+                        "duration_us": r.get("gpu__time_duration.sum"),
+                        "tensor_pipe_pct_elapsed": r.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")}
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -167,8 +213,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "forecast_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU path; value extrapolated from the bounded sample"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": CPU_SAMPLE_DESC},
+        "config": bench_config(args, int(os.environ.get("WORLD_SIZE", str(args.gpus)))),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": CPU_SAMPLE_DESC,
+                         "note": "CPU path; value extrapolated from the bounded sample to the 25 encodes + 24 decodes of a sequence"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -260,6 +307,23 @@ def run_b200_arm(args):
     launches = _cabi.launch_count() - launches0
     ms = e0.elapsed_time(e1)
     tsum = timer.summary()
+    sec = timer.secondary()
+    # ---- on-device check of the count all-reduce: the NCCL-reduced struct must equal the int64 sum of the
+    # ranks' own partials, and cover world x local elements
+    parity_check = None
+    if world > 1:
+        local = step_device()[0]
+        reduced = M.all_reduce_partials(local)
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        ni = M._N_INT
+        want_i = torch.stack([g[:ni] for g in gathered]).sum(0)
+        want_f = torch.stack([g[ni:].view(torch.float64) for g in gathered]).sum(0)
+        ok = bool(torch.equal(reduced[:ni], want_i)) and bool(torch.allclose(reduced[ni:].view(torch.float64), want_f, rtol=1e-12))
+        ok = ok and int(reduced[96].item()) == world * int(local[96].item()) and int(reduced[99].item()) == world * B * T_OUT
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        parity_check = "ok" if int(okt.item()) == 1 else "FAILED"
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -298,13 +362,20 @@ def run_b200_arm(args):
         fps = frames_total / (ms / 1e3)
         fps_e2e = frames_total / (ms_e2e / 1e3)
         achieved = tsum["nominal_flops"] / (tsum["ms"] / 1e3) / 1e12 if tsum["ms"] > 0 else 0.0
+        executed = tsum["executed_flops"] / (tsum["ms"] / 1e3) / 1e12 if tsum["ms"] > 0 else 0.0
+        traffic = ncu_traffic(["r2_*conv_gemm*n256*raw.csv", "r1_prof_final4_n256_raw.csv"])
+        traffic128 = ncu_traffic(["r2_*conv_gemm*n128*raw.csv", "r1_prof_final4_n128_raw.csv"])
+        secondary = {}
+        for name, d in sec.items():
+            gbs = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
+            secondary[name] = {"bound": "hbm", "gbs": gbs, "frac": gbs / peaks["hbm"], "launches": d["launches"],
+                               "us_per_launch": 1e3 * d["ms"] / max(d["launches"], 1),
+                               "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1)}
         line = {
             "metric": "forecast_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames_per_call": args.frames_per_call,
-                       "posterior": "mode", "l2": "inputs (118 MB uint8 + GB-scale activations) larger than the 126 MB L2",
-                       "parallelism": f"dp{world} (sequence shards, one all-reduce of the 864-byte partials)"},
+            "config": bench_config(args, world),
             "clocks": clocks,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(host.numel()),
                     "d2h_bytes_per_step": 108 * 8 + 4, "ms_per_step": ms_e2e / args.steps},
@@ -312,21 +383,23 @@ def run_b200_arm(args):
             "roofline": {
                 "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                # `achieved` aggregates ~4800 launches of different layer shapes; `traffic` is the DRAM bytes of ONE launch of
-                # the dominant variant (conv_gemm<256> HALO pair kernel, 256->256 @192^2, 8 frames) from its `ncu --set
-                # full` capture; the second capture covers the other large variant
-                "traffic": 258.4e6,
-                "traffic_ncu": {"conv_gemm<256> gn 256->256 @192^2 x 8 frames": {"dram_bytes": 258.4e6, "algorithmic_bytes": 302.0e6,
-                                                                              "tensor_pipe_active_pct": 91.9},
-                                "conv_gemm<128> gn 128->128 @384^2 x 8 frames": {"dram_bytes": 553.1e6, "algorithmic_bytes": 604.0e6,
-                                                                               "tensor_pipe_active_pct": 70.5},
-                                "source": "profiles/r1_prof_final4_n256_raw.csv, r1_prof_final4_n128_raw.csv"},
-                "peak_source": peaks["which"],
+                # `achieved` / `frac` use the NOMINAL 2*M*N*K of the reference layers; `executed_tflops` /
+                # `frac_executed` count the MMA work really issued (sub-pixel upsample: 2.25x fewer MACs; identity-tap
+                # residuals: a few more). `traffic`: DRAM bytes of ONE launch of the dominant variant, read from the
+                # committed `ncu --set full` raw export named in traffic_ncu[*].source.
+                "executed_tflops": executed, "frac_executed": executed / peaks["tflops"],
+                "traffic": traffic["dram_bytes"] if traffic else None,
+                "traffic_ncu": {"n256": traffic, "n128": traffic128},
+                "secondary": secondary,
+                "peak_source": peaks["which"], "hbm_peak_gbs": peaks["hbm"],
                 "launches_timed": tsum["launches"], "kernel_ms_per_step": tsum["ms"] / args.steps,
                 "kernel_share_of_step": tsum["ms"] / ms if ms > 0 else None,
                 "step_tflops_nominal": fps * GF_PER_FORECAST_FRAME / 1e3 / world,
                 "step_frac_of_peak": fps * GF_PER_FORECAST_FRAME / 1e3 / world / peaks["tflops"],
+                "step_frac_of_peak_executed": (fps * GF_PER_FORECAST_FRAME / 1e3 / world / peaks["tflops"]
+                                               * (tsum["executed_flops"] / tsum["nominal_flops"]) if tsum["nominal_flops"] else None),
             },
+            "parity_check": parity_check,
             "scores": {k: scores[k] for k in ("CSI_0", "CSI_3", "SSIM", "CRPS", "POD_0", "FAR_0", "MSE")},
         }
         if args.cpu_baseline and world == 1:

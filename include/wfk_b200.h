@@ -30,13 +30,17 @@ enum wfk_status {
   WFK_ERR_INVALID = -1,     /* bad argument / unsupported shape                      */
   WFK_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed (see wfk_last_error) */
   WFK_ERR_NO_DEVICE = -3,   /* no sm_100 device visible                              */
-  WFK_ERR_NOT_INIT = -4     /* wfk_init has not been called                          */
+  WFK_ERR_NOT_INIT = -4,    /* wfk_init has not been called for the targeted device  */
+  WFK_ERR_NONFINITE = -5    /* an activation left the fp16 range (inf / NaN detected) */
 };
 
 const char* wfk_strerror(int status);
 const char* wfk_last_error(void);     /* detail string of the most recent failure (thread-local) */
 int wfk_abi_version(void);
-/* Select the device, check compute capability 10.x, resolve cuTensorMapEncodeTiled. */
+/* Register `device` with the library: check compute capability 10.x, create its context, resolve
+ * cuTensorMapEncodeTiled. May be called for any number of devices, from any thread; the caller's current
+ * device is left unchanged. Every other entry point takes its device from its `stream` argument (plan creation:
+ * from the operand pointers), makes it current for the duration of the call and restores the caller's. */
 int wfk_init(int device);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t wfk_launch_count(void);

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128, 1) debug_shifted_mma_kernel(const __grid_
 
 extern "C" int wfk_debug_shifted_mma(const void* a_halo, int pitch, int rows, const void* b, int r, int s,
                                      int base_offset, float* d, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(a_halo && b && d, "null pointer");
   WFK_REQUIRE(pitch >= 10 && pitch <= 32 && rows >= 18 && rows <= 64, "bad halo shape");
   wfk::DebugMmaParams p{};
@@ -97,10 +97,10 @@ extern "C" int wfk_debug_shifted_mma(const void* a_halo, int pitch, int rows, co
   p.base_offset = base_offset;
   p.d = d;
   const size_t smem = 1024 + ((static_cast<size_t>(pitch) * rows * 128 + 1023) & ~size_t(1023)) + 128 * 128 + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static wfk::PerDeviceOnce attr_once;
+  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::debug_shifted_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_lock.finished();
   }
   wfk::debug_shifted_mma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
   return wfk::launched("debug_shifted_mma_kernel");

@@ -1,14 +1,25 @@
-"""Probe: shifted-window UMMA A descriptors on a TMA-written halo tile (see csrc/debug_mma.cu)."""
+"""Probe: shifted-window UMMA A descriptors on a TMA-written halo tile (scripts/probes/debug_mma.cu).
+Not part of libwfk_b200.so: the probe kernel is built here into its own library together with csrc/core.cu."""
 import ctypes as C
 import os
+import subprocess
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
 import torch
 
 from weatherforecastingtoolkit_b200 import _cabi
 
-lib = _cabi.init(0)
+CSRC = os.path.join(ROOT, "weatherforecastingtoolkit_b200", "csrc")
+SO = os.path.join(HERE, "libwfk_probe.so")
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                       "-cudart", "static", "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-o", SO,
+                       os.path.join(HERE, "debug_mma.cu"), os.path.join(CSRC, "core.cu")])
+lib = C.CDLL(SO)
+lib.wfk_init.argtypes = [C.c_int]
+assert lib.wfk_init(0) == 0
 fn = lib.wfk_debug_shifted_mma
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

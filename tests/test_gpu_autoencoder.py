@@ -246,6 +246,69 @@ def test_rollout_validation_step_vs_reference_golden(akl_weights, golden_akl, go
     assert 0.0 <= res["POD_0"] <= 1.0 and 0.0 <= res["FAR_0"] <= 1.0 and res["MSE"] > 0
 
 
+def test_rollout384_validation_step_vs_reference_golden(akl_weights):
+    """The HEADLINE configuration end to end (VERDICT r1 missing #2): one full Path-B validation_step at 384 x 384
+    (stage 25 uint8 frames -> encode 25 -> Linear 52->48 -> decode 12 pred + 12 target -> calc_metrics) against the
+    tensors the UNMODIFIED reference modules produced for the same seeds (tests/golden/make_golden_rollout384.py,
+    train.py:100-116): the encode error propagates through the predictor into both decodes, as in production."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+    from oracle import metrics_oracle as MO
+    from weatherforecastingtoolkit_b200 import metrics as M
+    from weatherforecastingtoolkit_b200.rollout import PathBNowcast
+    from weatherforecastingtoolkit_b200.synthetic import make_predictor_params, make_vil_sequences
+    gold = dict(np.load(os.path.join(GOLDEN, "rollout384_golden.npz")))
+    with open(os.path.join(GOLDEN, "rollout384_metrics.json")) as f:
+        gmeta = json.load(f)
+    cfg, sd = akl_weights
+    net = PathBNowcast(cfg, posterior="mode", frames_per_call=25)
+    net.autoencoder.autoencoder.load_state_dict(sd, strict=True)
+    w, b = make_predictor_params(seed=0)
+    net.predictor.weight.data.copy_(w)
+    net.predictor.bias.data.copy_(b)
+    net = net.to(DEV)
+    u8 = make_vil_sequences(1, 384, 384, 25, seed=gmeta["seed"]).to(DEV)
+    # stage by stage
+    from weatherforecastingtoolkit_b200.rollout import stage_vil
+    lat = net.autoencoder.encode(stage_vil(u8))
+    assert rel_l2(lat, torch.from_numpy(gold["latents"])) < 1e-2
+    pred_lat, tgt_lat, loss = net.predictor.rollout(lat)
+    assert rel_l2(pred_lat, torch.from_numpy(gold["pred_latents"])) < 1e-2
+    assert rel_l2(tgt_lat, torch.from_numpy(gold["tgt_latents"])) < 1e-2
+    # the public entry point
+    dp, dt, loss = net.validation_step(u8)
+    assert dp.shape == dt.shape == (1, 12, 1, 384, 384)
+    st, ph = gmeta["stride"], gmeta["phase"]
+    e_p = rel_l2(dp[..., ph::st, ph::st], torch.from_numpy(gold["decoded_pred_sub"]))
+    e_t = rel_l2(dt[..., ph::st, ph::st], torch.from_numpy(gold["decoded_tgt_sub"]))
+    print(f"rollout384 rel-L2 vs reference: forecast {e_p:.3e}, decoded target {e_t:.3e}")
+    assert e_p < 1e-2 and e_t < 1e-2          # north_star: forecasts within 1e-2 relative L2 of the fp32 reference
+    assert dp.double().norm().item() == pytest.approx(float(gold["decoded_pred_norm"]), rel=1e-3)
+    assert dt.double().norm().item() == pytest.approx(float(gold["decoded_tgt_norm"]), rel=1e-3)
+    assert np.allclose(dp.double().mean(dim=(0, 2, 3, 4)).cpu().numpy(), gold["decoded_pred_frame_mean"], atol=2e-3)
+    assert loss.item() == pytest.approx(float(gold["val_loss"]), rel=2e-2)
+    # scoring: counts bit-exact ON IDENTICAL FORECASTS; CSI / HSS then bit-identical; SSIM within 1e-3
+    got = M.metric_partials(dp, dt)
+    assert got.counts.tolist() == MO.integer_counts(dp.cpu(), dt.cpu()).tolist()
+    res = M.scores_from_partials(got, extended=True)
+    ref = MO.calc_metrics(dp.cpu(), dt.cpu())
+    for k, v in ref.items():
+        if k.startswith(("CSI", "HSS", "paper_CSI", "paper_HSS")):
+            assert res[k] == v, k
+        else:
+            assert res[k] == pytest.approx(v, abs=1e-3 if "SSIM" in k else 1e-5, rel=1e-5), k
+    # and the scores of the GPU forecasts land next to the reference's scores of ITS forecasts (they differ by e_p)
+    gm = gmeta["metrics"]
+    assert res["SSIM"] == pytest.approx(gm["SSIM"], abs=1e-2)
+    assert res["CRPS"] == pytest.approx(gm["CRPS"], abs=2e-3)
+    for i in range(6):
+        assert res[f"CSI_{i}"] == pytest.approx(gm[f"CSI_{i}"], abs=2e-2), i
+    tot = np.array(gmeta["counts"]).sum(axis=-1)
+    assert (got.counts.sum(axis=-1) == tot).all()
+
+
 def test_decode_run_to_run(model):
     """Same input twice: per-warp stats slots + fixed-order folds make the result reproducible up to
     the fp64 atomic order (1e-16), i.e. practically bit-identical."""

@@ -89,6 +89,79 @@ def test_metrics_vs_golden(lib, golden_metrics, name):
             assert got[k] == pytest.approx(v, abs=1e-6), k
 
 
+@pytest.mark.parametrize("name", METRIC_CASES)
+def test_metrics_ssim_psnr_vs_independent(lib, name):
+    """SSIM / PSNR of the fused kernel against the INDEPENDENT float64 implementation (oracle/ssim_independent.py:
+    scipy separable filtering over the valid region, no code shared with the torchmetrics restatement)."""
+    from oracle import ssim_independent as SI
+    from weatherforecastingtoolkit_b200 import metrics as M
+    p, t = metric_case_inputs(name)
+    got = M.calc_metrics(p.to(DEV), t.to(DEV))
+    pc, tc = p.clamp(0, 1).numpy(), t.clamp(0, 1).numpy()
+    assert got["SSIM"] == pytest.approx(SI.ssim(pc, tc), abs=1e-4)
+    assert got["PSNR"] == pytest.approx(SI.psnr_per_frame_mean(pc, tc), rel=1e-5)
+    # unclamped stand-alone functions, incl. negative targets (PSNR range through zero)
+    pd, td = (p - 0.3).to(DEV), (t - 0.3).to(DEV)
+    assert M.ssim(pd, td) == pytest.approx(SI.ssim((p - 0.3).numpy(), (t - 0.3).numpy()), abs=1e-4)
+    assert M.psnr(pd, td) == pytest.approx(SI.psnr_per_frame_mean((p - 0.3).numpy(), (t - 0.3).numpy()), rel=1e-5)
+
+
+def test_metrics_ssim_analytic_anchors(lib):
+    from weatherforecastingtoolkit_b200 import metrics as M
+    a, b = 0.25, 0.75
+    pa, tb = torch.full((1, 2, 1, 40, 56), a, device=DEV), torch.full((1, 2, 1, 40, 56), b, device=DEV)
+    closed = (2 * a * b + 1e-4) / (a * a + b * b + 1e-4)
+    assert M.ssim(pa, tb) == pytest.approx(closed, abs=1e-3)     # float32 noise floor of a constant image: ~3e-4 of C2
+    t = torch.rand(1, 1, 1, 32, 32)
+    t[0, 0, 0, 0, 0], t[0, 0, 0, 0, 1] = 0.0, 1.0
+    assert M.psnr((t + 0.1).to(DEV), t.to(DEV)) == pytest.approx(20.0, abs=1e-4)
+    tp = t * 0.5 + 0.25     # strictly positive target: range = t.max() - 0
+    assert M.psnr((tp + 0.1).to(DEV), tp.to(DEV)) == pytest.approx(10 * math.log10(0.75 ** 2 / 0.01), abs=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 1, 17, 23), (1, 1, 1, 33, 130), (2, 1, 1, 129, 67), (1, 1, 1, 70, 400), (1, 1, 1, 40, 800)])
+def test_metrics_ragged_and_wide_shapes(lib, shape):
+    """Odd widths (scalar-load path), widths beyond one 384-column strip (multi-strip path with 16-column overlaps),
+    heights that are not multiples of the 8-row chunk / 32-row segment."""
+    from oracle import metrics_oracle as MO
+    from weatherforecastingtoolkit_b200 import metrics as M
+    torch.manual_seed(sum(shape))
+    p, t = torch.rand(*shape) * 1.2 - 0.1, torch.rand(*shape) * 1.2 - 0.1
+    mp = M.metric_partials(p.to(DEV), t.to(DEV))
+    assert mp.counts.tolist() == MO.integer_counts(p, t).tolist()
+    want = MO.partials(p, t)
+    assert mp.n_elems.tolist() == list(want["n_elems"])
+    assert mp.ssim_sum == pytest.approx(want["ssim_sum"], abs=2e-5 * shape[0] * shape[1])
+    assert mp.psnr_sum == pytest.approx(want["psnr_sum"], rel=1e-5)
+    assert np.allclose(mp.abs_sum, want["abs_sum"], rtol=1e-5)
+    assert mp.sq_sum == pytest.approx(want["sq_sum"], rel=1e-5)
+
+
+def test_log_metrics_gpu(lib):
+    """rollout.log_metrics == pipeline.helpers.log_metrics (helpers.py:142-153): tag-prefixed calc_metrics dict handed
+    to pl_module.log_dict(on_step=True, on_epoch=True, sync_dist=True)."""
+    from weatherforecastingtoolkit_b200 import metrics as M
+    from weatherforecastingtoolkit_b200.rollout import log_metrics
+
+    class PL:
+        def __init__(self):
+            self.calls = []
+
+        def log_dict(self, d, **kw):
+            self.calls.append((d, kw))
+
+    p, t = metric_case_inputs("rand_2x10x64")
+    pd, td = p.to(DEV).requires_grad_(True), t.to(DEV)
+    pl = PL()
+    log_metrics(pd, td, "val", pl)
+    (d, kw), = pl.calls
+    want = M.calc_metrics(p.to(DEV), td)
+    assert list(d) == [f"val_{k}" for k in want] and len(d) == 56
+    assert all(d[f"val_{k}"] == v or (v != v and d[f"val_{k}"] != d[f"val_{k}"]) for k, v in want.items())
+    assert all(isinstance(v, float) for v in d.values())
+    assert kw == {"on_step": True, "on_epoch": True, "sync_dist": True}
+
+
 def test_metrics_standalone_functions(lib):
     from oracle import metrics_oracle as MO
     from weatherforecastingtoolkit_b200 import metrics as M

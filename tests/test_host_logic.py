@@ -162,3 +162,54 @@ def test_metric_accumulator_refuses_cpu_and_empty():
         acc.compute()
     with pytest.raises(RuntimeError):
         acc.update(torch.rand(1, 2, 1, 32, 32), torch.rand(1, 2, 1, 32, 32))
+
+
+def test_log_metrics_matches_reference_function(monkeypatch):
+    """rollout.log_metrics against the UNMODIFIED ``pipeline.helpers.log_metrics`` (helpers.py:142-153; extracted
+    with ast because helpers.py imports torch_lr_finder / lightning / matplotlib, none of which exist here): same
+    detach, same tag prefixing, same log_dict keyword arguments. With ``process_group`` the counts were already summed
+    over ranks, so Lightning must NOT average the scalars again: sync_dist=False."""
+    import ast
+    import os
+
+    from conftest import REFERENCE, has_reference
+    from weatherforecastingtoolkit_b200 import rollout
+
+    seen = {}
+
+    def fake_calc_metrics(pred, target, **kw):
+        seen["args"] = (pred, target, kw)
+        return {"CSI_0": 0.25, "SSIM": 0.5, "paper_CRPS": 0.125}
+
+    class PL:
+        def __init__(self):
+            self.calls = []
+
+        def log_dict(self, d, **kw):
+            self.calls.append((dict(d), kw))
+
+    monkeypatch.setattr(rollout.wf_metrics, "calc_metrics", fake_calc_metrics)
+    p = torch.rand(1, 2, 1, 16, 16, requires_grad=True)
+    t = torch.rand(1, 2, 1, 16, 16)
+    mine = PL()
+    rollout.log_metrics(p * 1.0, t, "val", mine)
+    assert mine.calls == [({"val_CSI_0": 0.25, "val_SSIM": 0.5, "val_paper_CRPS": 0.125},
+                           {"on_step": True, "on_epoch": True, "sync_dist": True})]
+    assert not seen["args"][0].requires_grad and seen["args"][2] == {"process_group": None}
+    grp = PL()
+    rollout.log_metrics(p, t, "test", grp, process_group="fake-group")
+    assert grp.calls[0][1]["sync_dist"] is False and list(grp.calls[0][0]) == ["test_CSI_0", "test_SSIM", "test_paper_CRPS"]
+    assert seen["args"][2] == {"process_group": "fake-group"}
+    # non-tensor inputs pass through untouched, as in the reference (isinstance checks)
+    rollout.log_metrics([1.0], [2.0], "x", PL())
+    assert seen["args"][0] == [1.0]
+    if not has_reference():
+        return
+    src = open(os.path.join(REFERENCE, "pipeline", "helpers.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "log_metrics")
+    ns = {"torch": torch, "calc_metrics": lambda a, b: fake_calc_metrics(a, b)}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "helpers.py", "exec"), ns)
+    ref = PL()
+    ns["log_metrics"](p * 1.0, t, "val", ref)
+    assert ref.calls == mine.calls
+    assert not seen["args"][0].requires_grad

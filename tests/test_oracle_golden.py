@@ -43,6 +43,34 @@ def test_rollout64_latent_algebra(golden_akl):
     np.testing.assert_allclose(tgt.numpy(), lat[:, 13:].numpy(), atol=1e-6)
 
 
+def test_rollout384_oracle_vs_reference_golden(akl_weights):
+    """HEADLINE-size golden (tests/golden/make_golden_rollout384.py, unmodified reference modules, 384 x 384): the
+    oracle reproduces one encoded frame, the predictor algebra and one decoded forecast frame of it (a bounded
+    subset: the full 25 + 24 frame pass is ~2.5 minutes of CPU and is what the GPU test compares against)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+    gold = dict(np.load(os.path.join(GOLDEN, "rollout384_golden.npz")))
+    with open(os.path.join(GOLDEN, "rollout384_metrics.json")) as f:
+        meta = json.load(f)
+    cfg, sd = akl_weights
+    u8 = make_vil_sequences(1, 384, 384, 25, seed=meta["seed"])
+    v = O.stage_vil(u8).permute(0, 3, 1, 2).unsqueeze(2)
+    lat = torch.from_numpy(gold["latents"])
+    w, b = make_predictor_params(seed=0)
+    with torch.no_grad():
+        z7 = O.akl_encode_moments(v[:, 7], sd, cfg)[:, :4]
+        pred, tgt, loss = O.predictor_rollout(lat, w, b)
+        d3 = O.akl_decode(torch.from_numpy(gold["pred_latents"][:, 3]), sd, cfg)
+    np.testing.assert_allclose(z7.numpy(), gold["latents"][:, 7], atol=2e-5)
+    np.testing.assert_allclose(pred.numpy(), gold["pred_latents"], atol=2e-6)
+    np.testing.assert_allclose(tgt.numpy(), gold["tgt_latents"], atol=2e-6)
+    assert loss.item() == pytest.approx(float(gold["val_loss"]), rel=1e-5)
+    st, ph = meta["stride"], meta["phase"]
+    np.testing.assert_allclose(d3[..., ph::st, ph::st].numpy(), gold["decoded_pred_sub"][:, 3], atol=5e-5)
+
+
 @pytest.mark.parametrize("name", METRIC_CASES)
 def test_metrics_oracle_vs_golden(golden_metrics, name):
     p, t = metric_case_inputs(name)

@@ -129,7 +129,7 @@ _PROTOTYPES = {
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 
 _lib = None
-_initialised_device = None
+_initialised_devices = set()   # devices registered with wfk_init (any number per process; the library is per-device)
 
 
 def lib_path() -> Path:
@@ -161,12 +161,14 @@ def check(status: int, what: str = "") -> None:
 
 
 def init(device: int = 0) -> C.CDLL:
-    """Load the library and bind it to a B200. Raises RuntimeError when no sm_100 GPU is present."""
-    global _initialised_device
+    """Load the library and register ``device`` (a B200) with it. Raises RuntimeError when it is not an sm_100 GPU.
+    Any number of devices may be registered; every call then runs on the device of the stream it is given and
+    leaves the caller's current device untouched."""
     lib = load()
-    if _initialised_device != device:
-        check(lib.wfk_init(int(device)), "wfk_init")
-        _initialised_device = device
+    device = int(device)
+    if device not in _initialised_devices:
+        check(lib.wfk_init(device), "wfk_init")
+        _initialised_devices.add(device)
     return lib
 
 

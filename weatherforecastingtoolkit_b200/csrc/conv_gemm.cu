@@ -61,6 +61,16 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kHaloRows = 18;
 constexpr int kHaloBStagesMax = 8;
 
+// Timing experiments (operand traffic removed, stores skipped, fewer CTA pairs ...) produce WRONG results by design:
+// they exist only in builds made with -DWFK_EXPERIMENTS and can never be switched on in the product library.
+#ifdef WFK_EXPERIMENTS
+#define WFK_XDBG(p) ((p).xform_debug)
+#define WFK_HINT_NS(p) ((p).wait_hint_ns)
+#else
+#define WFK_XDBG(p) 0
+#define WFK_HINT_NS(p) 0
+#endif
+
 struct ConvKernelParams {
   CUtensorMap a_map[2];
   CUtensorMap b_map[2];
@@ -338,7 +348,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           auto step = [&](const int seg, const int kb) {
             const CUtensorMap* am = &p.a_map[seg];
             
-              mbar_wait_h(&empty_bar[stage], phase ^ 1u, p.wait_hint_ns);
+              mbar_wait_h(&empty_bar[stage], phase ^ 1u, WFK_HINT_NS(p));
               uint8_t* sa = smem + stage * kStageBytes;
               // each CTA's box completes on its OWN barrier: its transform warps consume it first.
               // Source 1 (1x1 shortcut, centre tap only) needs no halo: a plain (8*MB) x 16 pixel box.
@@ -368,7 +378,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           const CUtensorMap* am = &p.a_map[tap.src];
           const CUtensorMap* bm = &p.b_map[tap.src];
           for (int kb = 0; kb < tap.kblocks; ++kb) {
-            mbar_wait_h(&empty_bar[stage], phase ^ 1u, p.wait_hint_ns);
+            mbar_wait_h(&empty_bar[stage], phase ^ 1u, WFK_HINT_NS(p));
             uint8_t* sa = smem + stage * kStageBytes;
             if (PAIR) {
               // The peer's bytes complete_tx on the leader's barrier too; the peer itself never arrives (a
@@ -556,9 +566,9 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
             for (int ti = 0; ti < ntaps; ++ti) {
               const int slab = (seg == 0 ? p.taps[t.phase * p.taps_per_phase + ti].b_slab : p.seg1_slab) +
                                t.frame * p.b_frame_mul;
-              mbar_wait_h(&bempty_bar[bstage], bphase ^ 1u, p.wait_hint_ns);
+              mbar_wait_h(&bempty_bar[bstage], bphase ^ 1u, WFK_HINT_NS(p));
               uint8_t* sbt = smem_b + bstage * kBBytes;
-              if (PAIR && p.xform_debug == 8) {   // timing experiment: no weight traffic at all (results are garbage)
+              if (PAIR && WFK_XDBG(p) == 8) {   // timing experiment: no weight traffic at all (results are garbage)
                 if (leader) mbar_arrive(&bfull_bar[bstage]);
               } else if (PAIR) {
                 if (leader) mbar_arrive_expect_tx(&bfull_bar[bstage], 2 * kBBytes);
@@ -596,8 +606,8 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       // K blocks of source 0 (every tap) interleaved with those of source 1 (fused 1x1 shortcut, centre tap): run_steps
       auto step = [&](const int seg, const int kb) {
         
-          mbar_wait_h(&full_bar[stage], phase, p.wait_hint_ns);
-          if (seg == 0 && (p.gn_table != nullptr || p.gn_stats != nullptr) && p.xform_debug != 2) {
+          mbar_wait_h(&full_bar[stage], phase, WFK_HINT_NS(p));
+          if (seg == 0 && (p.gn_table != nullptr || p.gn_stats != nullptr) && WFK_XDBG(p) != 2) {
             float ga[8], gb[8];
             if (p.gn_stats != nullptr) {
               // same arithmetic as wfk_gn_table: mean / rstd per group in double, (a, b) = (rstd*gamma, beta - mean*a)
@@ -680,7 +690,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
               for (int j = 0; j < kXfGroup; ++j) {
                 if (!ok[j]) continue;
                 __half2* h2 = reinterpret_cast<__half2*>(&u[j]);
-                if (p.xform_debug != 1) {
+                if (WFK_XDBG(p) != 1) {
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     // packed fp32x2 FMAs (sm_100): same rounding per component, half the issue slots
@@ -924,7 +934,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           }
         }
       }
-      mbar_wait_h(&tfull_bar[acc], acc_phase, p.wait_hint_ns);
+      mbar_wait_h(&tfull_bar[acc], acc_phase, WFK_HINT_NS(p));
       tc_fence_after();
       const uint32_t tlane =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * MB * BN);
@@ -1022,7 +1032,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           else chunk_group_stats<2>(v, valid, lane, dst);
         }
         if (!kCoalesce) {
-          if (valid && p.out_h != nullptr && p.xform_debug != 32) {
+          if (valid && p.out_h != nullptr && WFK_XDBG(p) != 32) {
             uint4* op = reinterpret_cast<uint4*>(p.out_h + base + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1035,7 +1045,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
               }
             }
           }
-        } else if (p.out_h != nullptr && p.xform_debug != 32) {   // 32: timing experiment without the fp16 stores
+        } else if (p.out_h != nullptr && WFK_XDBG(p) != 32) {   // 32: timing experiment without the fp16 stores
           uint4 up[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -1202,12 +1212,12 @@ template <int BN, bool PAIR, bool HALO, bool EPI = false>
 cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s) {
   using Cfg = ConvCfg<BN, PAIR, HALO>;
   auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, PAIR, HALO, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static wfk::PerDeviceOnce attr_once;
+  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(conv_smem_bytes<BN, PAIR, HALO, EPI>()));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_lock.finished();
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -1232,13 +1242,14 @@ cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s
 template <int BN, bool HALO>
 int max_active_pairs() {
   using Cfg = ConvCfg<BN, true, HALO>;
-  static int cached = -1;
-  if (cached >= 0) return cached;
+  static std::atomic<int> cached_dev[kMaxDevices];   // zero-initialised: 0 = not queried yet (per device)
+  const int dev = t_device < 0 ? 0 : t_device;
+  if (cached_dev[dev].load() > 0) return cached_dev[dev].load();
   auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, true, HALO, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(conv_smem_bytes<BN, true, HALO>()));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(g_num_sms);
+  cfg.gridDim = dim3(num_sms());
   cfg.blockDim = dim3(conv_threads(HALO, Cfg::kMB));
   cfg.dynamicSmemBytes = conv_smem_bytes<BN, true, HALO>();
   cudaLaunchAttribute attr[1];
@@ -1249,9 +1260,9 @@ int max_active_pairs() {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = g_num_sms / 2;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = num_sms() / 2;
   if (std::getenv("WFK_DEBUG")) fprintf(stderr, "[wfk] conv_gemm<%d,pair,halo=%d>: max active clusters = %d\n", BN, (int)HALO, n);
-  cached = n;
+  cached_dev[dev].store(n);
   return n;
 }
 
@@ -1264,6 +1275,7 @@ struct wfk_conv_plan {
   int halo;
   int epi;   // extended epilogue (activation / second activated output): EPI kernel variants
   int grid;
+  int device;
 };
 
 namespace {
@@ -1362,8 +1374,8 @@ bool pair_mode_enabled() {
 }  // namespace
 
 extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out) {
-  WFK_REQUIRE_INIT();
   WFK_REQUIRE(d != nullptr && out != nullptr, "null argument");
+  WFK_ENTER_PTR(d->a[0].ptr);   // the plan belongs to the device that holds its operands
   WFK_REQUIRE(d->n_total > 0 && d->n_total % 8 == 0, "n_total=%d must be a positive multiple of 8", d->n_total);
   WFK_REQUIRE(d->num_phases == 1 || d->num_phases == 4, "num_phases must be 1 or 4");
   WFK_REQUIRE(d->taps_per_phase >= 1 && d->num_phases * d->taps_per_phase <= WFK_MAX_TAPS, "too many taps");
@@ -1391,7 +1403,7 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   WFK_REQUIRE(plan != nullptr, "out of memory");
   wfk::ConvKernelParams& p = plan->params;
   plan->bn = (d->n_total % 256 == 0 || d->n_total > 256) ? 256 : 128;
-  plan->pair = (pair_mode_enabled() && wfk::g_num_sms % 2 == 0) ? 1 : 0;
+  plan->pair = (pair_mode_enabled() && wfk::num_sms() % 2 == 0) ? 1 : 0;
   if (d->stats != nullptr && d->n_total % 32 != 0) {
     delete plan;
     return wfk::fail(WFK_ERR_INVALID, "stats need n_total (%d) to be a multiple of 32 (one accumulator chunk)", d->n_total);
@@ -1451,8 +1463,12 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
     p.gn_cpg_log2 = l2;
     p.gn_inv_count = 1.0 / (static_cast<double>(cpg_in) * d->tile_h * d->tile_w);
   }
+  p.wait_hint_ns = 0;
+  p.xform_debug = 0;
+#ifdef WFK_EXPERIMENTS
   p.wait_hint_ns = std::getenv("WFK_WAIT_HINT") ? std::atoi(std::getenv("WFK_WAIT_HINT")) : 0;
   p.xform_debug = std::getenv("WFK_XFORM_DEBUG") ? std::atoi(std::getenv("WFK_XFORM_DEBUG")) : 0;
+#endif
   if ((d->gn_table != nullptr || d->gn_stats != nullptr) && !plan->halo) {
     delete plan;
     return wfk::fail(WFK_ERR_INVALID, "a fused GroupNorm+SiLU input (gn_table) needs a HALO-eligible 3x3 stride-1 convolution");
@@ -1515,21 +1531,26 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
     long use = pairs;
     // experiment knob: run on fewer CTA pairs (what a 4-CTA-cluster design would get: 66 of 74) to see how much of the
     // lost SMs the power cap gives back as clock
+#ifdef WFK_EXPERIMENTS
     if (const char* e = std::getenv("WFK_MAX_PAIRS")) {
       const long cap = std::atol(e);
       if (cap >= 1 && cap < use) use = cap;
     }
+#endif
     plan->grid = static_cast<int>(2 * (total_tiles < use ? total_tiles : use));
   } else {
-    plan->grid = static_cast<int>(total_tiles < wfk::g_num_sms ? total_tiles : wfk::g_num_sms);
+    plan->grid = static_cast<int>(total_tiles < wfk::num_sms() ? total_tiles : wfk::num_sms());
   }
+  plan->device = wfk::t_device;
   *out = plan;
   return WFK_OK;
 }
 
 extern "C" int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream) {
-  WFK_REQUIRE_INIT();
   WFK_REQUIRE(plan != nullptr, "null plan");
+  WFK_ENTER_STREAM(stream);
+  WFK_REQUIRE(plan->device == wfk::t_device, "plan was created on device %d, stream belongs to device %d", plan->device,
+              wfk::t_device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (plan->epi) {

@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(kCaThreads, 1) convattn_kernel(const float* __
 // weatherforecastingtoolkit_b200/predictors.py::ConvAttnModel._weight_pointers).
 extern "C" int wfk_convattn_forward(const float* x, int n, int cin, int layers, int latent_dim, const float* const* weights,
                                     int num_weights, float* z, float* recon, double* huber_sums, int mode, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(weights && z, "null pointer");
   WFK_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (encode + decode), 1 (encode only) or 2 (decode only)");
   WFK_REQUIRE(mode == 2 || x != nullptr, "x is required unless decoding from z");
@@ -520,11 +520,11 @@ extern "C" int wfk_convattn_forward(const float* x, int n, int cin, int layers, 
   }
   W.t0_w = next(), W.t0_b = next(), W.g2_w = next(), W.g2_b = next(), W.t1_w = next(), W.t1_b = next();
   const size_t smem = (static_cast<size_t>(3) * wfk::kCaBuf + 2 * wfk::kCaT + 3 * wfk::kCaD + 32) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static wfk::PerDeviceOnce attr_once;
+  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::convattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    attr_set = true;
+    attr_lock.finished();
   }
   wfk::convattn_kernel<<<n, wfk::kCaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       x, cin, layers, latent_dim, W, z, recon, huber_sums, mode != 2, mode != 1);

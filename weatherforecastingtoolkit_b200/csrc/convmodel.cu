@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kCmThreads, 1) convmodel_kernel(const float* _
 
 extern "C" int wfk_convmodel_forward(const float* x, int n, int cin, int latent_dim, const float* const* weights,
                                      float* z, float* recon, double* huber_sums, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(x && weights && z && recon, "null pointer");
   WFK_REQUIRE(n > 0 && cin >= 1 && cin <= 8 && latent_dim >= 1 && latent_dim <= 4096, "bad shape");
   for (int i = 0; i < 34; ++i) WFK_REQUIRE(weights[i] != nullptr, "weights[%d] is NULL", i);
@@ -228,10 +228,10 @@ extern "C" int wfk_convmodel_forward(const float* x, int n, int cin, int latent_
   W.out_w = weights[k++];
   W.out_b = weights[k++];
   const size_t smem = (static_cast<size_t>(2) * wfk::kCmC * 2304 + latent_dim) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static wfk::PerDeviceOnce attr_once;
+  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::convmodel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_lock.finished();
   }
   WFK_REQUIRE(smem <= 200 * 1024, "latent_dim too large");
   wfk::convmodel_kernel<<<n, wfk::kCmThreads, smem, static_cast<cudaStream_t>(stream)>>>(x, cin, latent_dim, W, z, recon,

@@ -4,9 +4,62 @@
 namespace wfk {
 thread_local char g_last_error[512] = "";
 std::atomic<int64_t> g_launches{0};
-int g_device = -1;
-int g_num_sms = 0;
+std::atomic<uint64_t> g_init_mask{0};
+int g_num_sms_dev[kMaxDevices] = {0};
+thread_local int t_device = -1;
 EncodeTiledFn g_encode_tiled = nullptr;
+static std::mutex g_init_mu;
+
+void DeviceScope::enter(int device) {
+  dev = device;
+  saved = t_device;
+  if (device < 0 || device >= kMaxDevices || !(g_init_mask.load(std::memory_order_acquire) & (1ull << device))) {
+    status = fail(WFK_ERR_NOT_INIT, "wfk_init(%d) was not called for the device this call targets", device);
+    dev = -2;
+    return;
+  }
+  cudaError_t e = cudaGetDevice(&prev);
+  if (e == cudaSuccess && prev != device) {
+    e = cudaSetDevice(device);
+    switched = (e == cudaSuccess);
+  }
+  if (e != cudaSuccess) {
+    status = fail(WFK_ERR_CUDA, "selecting device %d failed: %s", device, cudaGetErrorString(e));
+    dev = -2;
+    return;
+  }
+  t_device = device;
+}
+
+DeviceScope DeviceScope::from_stream(void* stream) {
+  int device = -1;
+  // the legacy / per-thread default streams report the calling thread's current device
+  cudaError_t e = cudaStreamGetDevice(static_cast<cudaStream_t>(stream), &device);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    e = cudaGetDevice(&device);
+  }
+  if (e != cudaSuccess) device = -1;
+  return DeviceScope(device);
+}
+
+DeviceScope DeviceScope::from_pointer(const void* device_ptr) {
+  int device = -1;
+  cudaPointerAttributes attr;
+  if (device_ptr != nullptr && cudaPointerGetAttributes(&attr, device_ptr) == cudaSuccess &&
+      (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged))
+    device = attr.device;
+  else
+    cudaGetLastError();
+  if (device < 0) cudaGetDevice(&device);
+  return DeviceScope(device);
+}
+
+DeviceScope::~DeviceScope() {
+  if (dev == -2) return;  // never entered (or moved from)
+  t_device = saved;
+  if (switched) cudaSetDevice(prev);
+}
 }  // namespace wfk
 
 extern "C" const char* wfk_strerror(int status) {
@@ -16,6 +69,7 @@ extern "C" const char* wfk_strerror(int status) {
     case WFK_ERR_CUDA: return "CUDA error";
     case WFK_ERR_NO_DEVICE: return "no sm_100 (B200) device";
     case WFK_ERR_NOT_INIT: return "wfk_init not called";
+    case WFK_ERR_NONFINITE: return "non-finite activation (fp16 range exceeded)";
     default: return "unknown status";
   }
 }
@@ -24,28 +78,39 @@ extern "C" const char* wfk_last_error(void) { return wfk::g_last_error; }
 extern "C" int wfk_abi_version(void) { return WFK_ABI_VERSION; }
 extern "C" int64_t wfk_launch_count(void) { return wfk::g_launches.load(); }
 
+// Registers `device` with the library (any number of devices, from any thread). The caller's current device is left
+// as it was: every later entry point selects the device of its stream / pointers itself.
 extern "C" int wfk_init(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0)
     return wfk::fail(WFK_ERR_NO_DEVICE, "cudaGetDeviceCount: %s (count=%d)", cudaGetErrorString(e), count);
-  if (device < 0 || device >= count) return wfk::fail(WFK_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  if (device < 0 || device >= count || device >= wfk::kMaxDevices)
+    return wfk::fail(WFK_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  std::lock_guard<std::mutex> lock(wfk::g_init_mu);
+  if (wfk::g_init_mask.load() & (1ull << device)) return WFK_OK;
   cudaDeviceProp prop;
   WFK_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return wfk::fail(WFK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major,
                      prop.minor);
+  int prev = -1;
+  WFK_CUDA_CHECK(cudaGetDevice(&prev));
   WFK_CUDA_CHECK(cudaSetDevice(device));
-  WFK_CUDA_CHECK(cudaFree(0));
-  if (wfk::g_encode_tiled == nullptr) {
+  cudaError_t ce = cudaFree(0);   // creates the primary context
+  if (ce == cudaSuccess && wfk::g_encode_tiled == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
-    WFK_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
+    ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (ce == cudaSuccess && (fn == nullptr || qres != cudaDriverEntryPointSuccess)) {
+      cudaSetDevice(prev);
       return wfk::fail(WFK_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    wfk::g_encode_tiled = reinterpret_cast<wfk::EncodeTiledFn>(fn);
+    }
+    if (ce == cudaSuccess) wfk::g_encode_tiled = reinterpret_cast<wfk::EncodeTiledFn>(fn);
   }
-  wfk::g_num_sms = prop.multiProcessorCount;
-  wfk::g_device = device;
+  if (prev != device) cudaSetDevice(prev);
+  if (ce != cudaSuccess) return wfk::fail(WFK_ERR_CUDA, "initialising device %d failed: %s", device, cudaGetErrorString(ce));
+  wfk::g_num_sms_dev[device] = prop.multiProcessorCount;
+  wfk::g_init_mask.fetch_or(1ull << device, std::memory_order_release);
   return WFK_OK;
 }

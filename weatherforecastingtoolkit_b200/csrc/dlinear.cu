@@ -125,7 +125,7 @@ extern "C" int wfk_dlinear(const float* x, int64_t x_batch_stride, const float* 
                            const float* w_trend, const float* b_trend, int nb, int seq_len, int pred_len, int channels,
                            int group, int kernel_size, int individual, int framed, float* pred, float* tgt,
                            double* loss_sums, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(x && w_seasonal && b_seasonal && w_trend && b_trend && pred, "null pointer");
   WFK_REQUIRE(nb > 0 && seq_len > 0 && pred_len > 0 && channels > 0, "empty problem");
   WFK_REQUIRE(kernel_size >= 1 && (kernel_size & 1), "kernel_size=%d must be odd (the reference pads (k-1)/2 per side)",
@@ -136,10 +136,10 @@ extern "C" int wfk_dlinear(const float* x, int64_t x_batch_stride, const float* 
   const size_t smem = (2 * static_cast<size_t>(seq_len) * wfk::kDlThreads +
                        (individual ? 0 : 2 * static_cast<size_t>(pred_len) * (seq_len + 1))) * sizeof(float);
   WFK_REQUIRE(smem <= 200 * 1024, "DLinear too large for shared memory (seq_len=%d pred_len=%d)", seq_len, pred_len);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static wfk::PerDeviceOnce attr_once;
+  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::dlinear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_lock.finished();
   }
   const int64_t total = static_cast<int64_t>(nb) * channels;
   const unsigned blocks = static_cast<unsigned>((total + wfk::kDlThreads - 1) / wfk::kDlThreads);

@@ -232,12 +232,12 @@ int launch_tail_tc(const __half* x, const double* stats, const float* gamma, con
   constexpr int C = KSTEPS * 16;
   const size_t smem = (2 * C + kTcMTiles * 16 * 9) * sizeof(float) + static_cast<size_t>(KSTEPS) * 2 * 32 * 8 +
                       static_cast<size_t>(kTcWarps) * 16 * (C + 8) * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static wfk::PerDeviceOnce attr_once;
+  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     cudaError_t e = cudaFuncSetAttribute(gn_silu_conv3x3_c1_tc_kernel<KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return fail(WFK_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_lock.finished();
   }
   const int tiles_x = (w + kOT - 1) / kOT;
   dim3 grid((tiles_x + kTcStrip - 1) / kTcStrip, (h + kOT - 1) / kOT, n);
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kOutThreads) gn_silu_conv3x3_c1_kernel(
 extern "C" int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const float* gamma, const float* beta, int n,
                                       int h, int w, int c, int groups, float eps, const float* weight, float bias,
                                       float* out, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(x && stats && gamma && beta && weight && out, "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0, "bad shape");
   WFK_REQUIRE(c % 8 == 0 && c > 0 && c <= 1024 && c % groups == 0 && groups <= 256, "unsupported c=%d groups=%d", c, groups);
@@ -350,10 +350,10 @@ extern "C" int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const 
     if (c == 256) return wfk::launch_tail_tc<16>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
   }
   const size_t smem = (static_cast<size_t>(c) * 11 + wfk::kOH * wfk::kOH * 9 + 2 * groups) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static wfk::PerDeviceOnce attr_once;
+  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::gn_silu_conv3x3_c1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+    attr_lock.finished();
   }
   WFK_REQUIRE(smem <= 100 * 1024, "channel count too large for shared memory");
   dim3 grid((w + wfk::kOT - 1) / wfk::kOT, (h + wfk::kOT - 1) / wfk::kOT, n);

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) render_panels_kernel(const float* __restr
 extern "C" int wfk_render_panels(const float* pred, const float* tgt, int64_t count, const uint8_t* lut_vil_rgba,
                                  const uint8_t* lut_diff_rgba, uint8_t* tgt_u8, uint8_t* pred_u8, uint8_t* diff_u8,
                                  uint8_t* tgt_rgba, uint8_t* pred_rgba, uint8_t* diff_rgba, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(pred && tgt && lut_vil_rgba && lut_diff_rgba, "null pointer");
   WFK_REQUIRE(count > 0, "empty problem");
   auto aligned = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
@@ -88,7 +88,7 @@ extern "C" int wfk_render_panels(const float* pred, const float* tgt, int64_t co
               "outputs must be 4-byte (u8) / 16-byte (rgba) aligned");
   const int64_t n4 = (count + 3) >> 2;
   int64_t blocks = (n4 + 255) / 256;
-  const int64_t cap = static_cast<int64_t>(wfk::g_num_sms) * 16;  // grid-stride: 8 CTAs x 2 waves per SM
+  const int64_t cap = static_cast<int64_t>(wfk::num_sms()) * 16;  // grid-stride: 8 CTAs x 2 waves per SM
   if (blocks > cap) blocks = cap;
   wfk::render_panels_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       pred, tgt, n4, count, reinterpret_cast<const uint32_t*>(lut_vil_rgba), reinterpret_cast<const uint32_t*>(lut_diff_rgba),

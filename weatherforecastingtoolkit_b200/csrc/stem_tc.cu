@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_s
 
 extern "C" int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w, int ones_plane, const void* weight_h,
                                    const float* bias, int cout, void* out, double* stats, int cpg, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(in && weight_h && bias && out, "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && cin >= 1, "bad shape");
   const int K = (cin + (ones_plane ? 1 : 0)) * 9;
@@ -203,7 +203,7 @@ extern "C" int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w
   const int mtiles = (h * w + 15) / 16;
   int tpw = 8;
   while (tpw > 1 && static_cast<int64_t>((mtiles + wfk::kStemTcWarps * tpw - 1) / (wfk::kStemTcWarps * tpw)) * n * (cout / wfk::kStemTcN) <
-                        4 * static_cast<int64_t>(wfk::g_num_sms))
+                        4 * static_cast<int64_t>(wfk::num_sms()))
     tpw >>= 1;
   dim3 grid((mtiles + wfk::kStemTcWarps * tpw - 1) / (wfk::kStemTcWarps * tpw), n, cout / wfk::kStemTcN);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

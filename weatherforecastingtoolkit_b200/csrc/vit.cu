@@ -192,14 +192,14 @@ __global__ void __launch_bounds__(256) bcast_add_rows_kernel(const float* __rest
 
 inline unsigned grid_for(int64_t total, int per_block) {
   int64_t blocks = (total + per_block - 1) / per_block;
-  const int64_t cap = static_cast<int64_t>(g_num_sms) * 16;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
   return static_cast<unsigned>(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
 }
 
 }  // namespace wfk
 
 extern "C" int wfk_patchify16(const float* img, int n, int h, int w, void* rows, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(img && rows && n > 0 && h > 0 && w > 0 && h % 16 == 0 && w % 16 == 0, "bad argument (h, w multiples of 16)");
   const int64_t total = static_cast<int64_t>(n) * h * w;
   wfk::patchify16_kernel<<<wfk::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -208,7 +208,7 @@ extern "C" int wfk_patchify16(const float* img, int n, int h, int w, void* rows,
 }
 
 extern "C" int wfk_unpatchify16(const float* rows, int n, int h, int w, float* img, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(img && rows && n > 0 && h > 0 && w > 0 && h % 16 == 0 && w % 16 == 0, "bad argument (h, w multiples of 16)");
   const int64_t total = static_cast<int64_t>(n) * h * w;
   wfk::unpatchify16_kernel<<<wfk::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, n, h, w, img);
@@ -216,15 +216,15 @@ extern "C" int wfk_unpatchify16(const float* rows, int n, int h, int w, float* i
 }
 
 extern "C" int wfk_mha_small(const void* qkv, int n, int tokens, int d_model, int heads, void* out, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(qkv && out && n > 0 && n <= 65535, "bad argument");
   WFK_REQUIRE(tokens >= 1 && tokens <= wfk::kMhaT, "tokens=%d unsupported (1..%d)", tokens, wfk::kMhaT);
   WFK_REQUIRE(heads >= 1 && d_model == heads * wfk::kMhaD, "d_model=%d must be heads (%d) x 64", d_model, heads);
   constexpr size_t smem = (3 * wfk::kMhaT * (wfk::kMhaD + 1) + wfk::kMhaT * (wfk::kMhaT + 1)) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static wfk::PerDeviceOnce attr_once;
+  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::mha_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_set = true;
+    attr_lock.finished();
   }
   wfk::mha_small_kernel<<<dim3(heads, n), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(qkv), tokens, d_model, 0.125f, static_cast<__half*>(out));
@@ -233,7 +233,7 @@ extern "C" int wfk_mha_small(const void* qkv, int n, int tokens, int d_model, in
 
 extern "C" int wfk_cross_encode_attn(const float* q_scaled, const void* kv, int n, int tokens, int d_latent, int heads,
                                      void* out, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(q_scaled && kv && out && n > 0 && n <= 65535, "bad argument");
   WFK_REQUIRE(tokens >= 1 && tokens <= 128 && heads >= 1 && d_latent % heads == 0, "bad shape");
   wfk::cross_encode_attn_kernel<<<dim3(heads, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -243,7 +243,7 @@ extern "C" int wfk_cross_encode_attn(const float* q_scaled, const void* kv, int 
 
 extern "C" int wfk_layernorm_rows(const float* x, int64_t rows, int d, const float* gamma, const float* beta, float eps,
                                   void* out_h, float* out_f, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(x && gamma && beta && (out_h || out_f) && rows > 0 && d > 0, "bad argument");
   const int64_t blocks = (rows + 7) / 8;
   wfk::layernorm_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -252,7 +252,7 @@ extern "C" int wfk_layernorm_rows(const float* x, int64_t rows, int d, const flo
 }
 
 extern "C" int wfk_bcast_add_rows(const float* vec, const float* pos, int n, int tokens, int d, void* out, void* stream) {
-  WFK_REQUIRE_INIT();
+  WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(vec && pos && out && n > 0 && tokens > 0 && d > 0, "bad argument");
   const int64_t total = static_cast<int64_t>(n) * tokens * d;
   wfk::bcast_add_rows_kernel<<<wfk::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

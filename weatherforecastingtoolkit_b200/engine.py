@@ -26,27 +26,64 @@ GN_EPS = 1e-6  # resnet_eps passed by Encoder/Decoder (vae.py:41,57,128)
 
 
 class KernelTimer:
-    """Optional per-launch CUDA-event timing of the tensor-core kernel (bench.py's roofline leg).
-    Events are recorded on the launching stream around every conv-GEMM launch; ``summary()`` must be
-    called after a synchronize. ``flops`` are NOMINAL (2*M*N*K of the reference layer), not what the
-    sub-pixel decomposition actually executes."""
+    """Optional per-launch CUDA-event timing (bench.py's roofline legs). Events are recorded on the launching stream
+    around every conv-GEMM launch and around the HBM-bound passes (staging, predictor, metrics); ``summary()`` /
+    ``secondary()`` must be called after a synchronize. ``flops`` are NOMINAL (2*M*N*K of the reference layer);
+    ``executed`` is the MMA work the kernel really issues (the 4-phase sub-pixel upsample does 2.25x fewer MACs than
+    the nominal 3x3 convolution on the upsampled tensor, the identity-tap residual adds some)."""
 
     def __init__(self, all_ops: bool = False):
         self.records = []  # (what, nominal_flops, start_event, end_event)
+        self.executed = []  # executed flops, parallel to records
         self.all_ops = all_ops  # also time the non-GEMM kernels (bench.py --breakdown)
+        self.passes = []   # (name, algorithmic_bytes, start_event, end_event): HBM-bound passes
 
-    def record(self, what, flops, start, end):
+    def record(self, what, flops, start, end, executed=None):
         self.records.append((what, flops, start, end))
+        self.executed.append(flops if executed is None else executed)
+
+    def record_pass(self, name, nbytes, start, end):
+        self.passes.append((name, nbytes, start, end))
 
     def summary(self):
-        tot_ms, tot_flops, n = 0.0, 0.0, 0
-        for _, fl, s, e in self.records:
+        tot_ms, tot_flops, tot_exec, n = 0.0, 0.0, 0.0, 0
+        for (_, fl, s, e), ex in zip(self.records, self.executed):
             if not fl:
                 continue
             tot_ms += s.elapsed_time(e)
             tot_flops += fl
+            tot_exec += ex
             n += 1
-        return {"launches": n, "ms": tot_ms, "nominal_flops": tot_flops}
+        return {"launches": n, "ms": tot_ms, "nominal_flops": tot_flops, "executed_flops": tot_exec}
+
+    def secondary(self):
+        """{pass name: {launches, ms, bytes}} of the HBM-bound passes."""
+        out = {}
+        for name, nbytes, s, e in self.passes:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["bytes"] += nbytes
+        return out
+
+
+class timed_pass:
+    """``with timed_pass(name, algorithmic_bytes):`` around an HBM-bound launch; a no-op unless bench.py set TIMER."""
+
+    def __init__(self, name: str, nbytes: float):
+        self.name, self.nbytes, self.timer = name, nbytes, TIMER
+
+    def __enter__(self):
+        if self.timer is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.timer is not None:
+            self.e1.record()
+            self.timer.record_pass(self.name, self.nbytes, self.e0, self.e1)
+        return False
 
 
 TIMER: Optional[KernelTimer] = None  # set by bench.py
@@ -243,17 +280,22 @@ class AKLEngine:
         prog = self._program("enc", tuple(x.shape))
         return prog.run(x)
 
-    def decode(self, z: torch.Tensor) -> torch.Tensor:
-        """z [N, lc, h, w] fp32 cuda -> [N, out_ch, 8h, 8w] fp32."""
+    def decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """z [N, lc, h, w] fp32 cuda -> [N, out_ch, 8h, 8w] fp32 (written into ``out`` when given: a contiguous
+        fp32 CUDA tensor of that shape, e.g. a slice of the caller's [B*T, ...] result)."""
         prog = self._program("dec", tuple(z.shape))
-        return prog.run(z)
+        return prog.run(z, out=out)
+
+    MAX_PLANS = 4   # programs own their activation pools (GBs at 384 x 384): keep the most recent shapes only
 
     def _program(self, kind: str, shape: Tuple[int, ...]) -> "_Program":
         key = (kind, shape)
-        prog = self._plans.get(key)
+        prog = self._plans.pop(key, None)
         if prog is None:
+            while len(self._plans) >= self.MAX_PLANS:
+                self._plans.pop(next(iter(self._plans)))   # least recently used (dicts keep insertion order)
             prog = _Program(self, kind, shape)
-            self._plans[key] = prog
+        self._plans[key] = prog
         return prog
 
 
@@ -287,22 +329,29 @@ class _Program:
             pass
 
     # ------------------------------------------------------------------ running
-    def run(self, x: torch.Tensor) -> torch.Tensor:
+    def run(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Single-stream use: the bound buffers are shared by every call of this program."""
         if x.dtype != torch.float32 or not x.is_cuda:
             raise TypeError("expected a float32 CUDA tensor")
+        if out is not None and (out.shape != self.output.shape or out.dtype != torch.float32 or not out.is_contiguous()
+                                or out.device != self.output.device):
+            raise ValueError(f"out must be a contiguous float32 tensor of shape {tuple(self.output.shape)} on {self.dev}")
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.input.copy_(x)
         self.stats_arena.zero_()
         timer = TIMER
-        for fn, args, what, flops in self.ops:
+        for fn, args, what, flops, executed in self.ops:
             if timer is not None and (flops or timer.all_ops):
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
                 _cabi.check(fn(*args, stream), what)
                 ev1.record()
-                timer.record(what, flops, ev0, ev1)
+                timer.record(what, flops, ev0, ev1, executed)
             else:
                 _cabi.check(fn(*args, stream), what)
+        if out is not None:
+            out.copy_(self.output)
+            return out
         return self.output.clone()
 
     # ------------------------------------------------------------------ helpers
@@ -313,14 +362,19 @@ class _Program:
             raise RuntimeError("stats arena exhausted")
         return s
 
-    def _add(self, fn, args, what, flops=0.0):
-        self.ops.append((fn, tuple(args), what, float(flops)))
+    def _add(self, fn, args, what, flops=0.0, executed=None):
+        self.ops.append((fn, tuple(args), what, float(flops), float(flops if executed is None else executed)))
 
-    def _conv_plan(self, desc: ConvDesc, what: str, nominal_flops: float):
+    def _conv_plan(self, desc: ConvDesc, what: str, nominal_flops: float, executed_flops: Optional[float] = None):
+        """``executed_flops``: MMA work really issued when it differs from the nominal 2*M*N*K of the reference layer
+        (defaults to: pixels x n_total x 64 x sum of the taps' K blocks of one phase, times the phases)."""
         h = C.c_void_p()
         _cabi.check(self.lib.wfk_conv_plan_create(C.byref(desc), C.byref(h)), f"conv_plan_create[{what}]")
         self.plans.append(h)
-        self._add(self.lib.wfk_conv_plan_run, (h,), what, nominal_flops)
+        if executed_flops is None:
+            kb = sum(desc.taps[i].kblocks for i in range(desc.taps_per_phase))
+            executed_flops = 2.0 * desc.n_frames * desc.tile_h * desc.tile_w * desc.n_total * 64 * kb * desc.num_phases
+        self._add(self.lib.wfk_conv_plan_run, (h,), what, nominal_flops, executed_flops)
 
     @staticmethod
     def _view_nhwc(desc_view, t: torch.Tensor, n, h, w, c, pitch_c=None):

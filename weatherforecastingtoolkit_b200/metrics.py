@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+from . import engine as _engine
 
 _eps = 1e-8
 THRESHOLDS = [16 / 255, 74 / 255, 133 / 255, 160 / 255, 181 / 255, 219 / 255]  # metrics.py:107
@@ -118,8 +119,9 @@ def metric_partials_device(pred: torch.Tensor, target: torch.Tensor, thresholds:
             _workspaces.clear()
             _workspaces[key] = ws
         part = out if done == 0 else torch.empty_like(out)
-        _cabi.check(lib.wfk_metrics(p[done:].data_ptr(), t[done:].data_ptr(), nf, h, w, thr, len(thresholds),
-                                    1 if clamp else 0, part.data_ptr(), ws.data_ptr(), ws_bytes, stream), "wfk_metrics")
+        with _engine.timed_pass("metrics", 8.0 * nf * h * w):   # algorithmic traffic: pred + target read once
+            _cabi.check(lib.wfk_metrics(p[done:].data_ptr(), t[done:].data_ptr(), nf, h, w, thr, len(thresholds),
+                                        1 if clamp else 0, part.data_ptr(), ws.data_ptr(), ws_bytes, stream), "wfk_metrics")
         if done:
             acc = _add_device(out, part)
             out = acc

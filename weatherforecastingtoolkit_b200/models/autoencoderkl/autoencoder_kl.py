@@ -149,10 +149,21 @@ class AutoencoderKL(nn.Module):
         moments = self._get_engine(x.device).encode_moments(x)
         return DiagonalGaussianDistribution(moments)
 
+    def repack(self) -> None:
+        """Drop the packed fp16 weights: call after writing parameters through ``.data`` (EMA swaps, manual init), which
+        does not bump ``Parameter._version`` and is therefore invisible to the automatic check in ``_get_engine``."""
+        self._engine = None
+        self._engine_key = None
+
     @torch.no_grad()
-    def _decode(self, z: torch.Tensor) -> torch.Tensor:
+    def _decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         z = self._check_input(z)
-        return self._get_engine(z.device).decode(z)
+        return self._get_engine(z.device).decode(z, out=out)
+
+    def decode_into(self, z: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """``decode`` writing into a caller-owned contiguous fp32 tensor (no reference counterpart: saves the
+        clone + ``torch.cat`` of the per-chunk loop in ``rollout.Autoencoder.decode``)."""
+        return self._decode(z, out=out)
 
     def enable_slicing(self):
         self.use_slicing = True

@@ -13,7 +13,7 @@ from typing import Dict, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from . import _cabi
+from . import _cabi, engine
 from . import metrics as wf_metrics
 from .models.autoencoderkl import AutoencoderKL
 from .synthetic import INPUT_FRAMES, PRED_FRAMES
@@ -40,8 +40,9 @@ def stage_vil(batch_u8_nhwt: torch.Tensor, dtype: torch.dtype = torch.float32) -
         raise ValueError("dtype must be float32 or float16")
     out = torch.empty((n, t, 1, h, w), dtype=dtype, device=x.device)
     stream = torch.cuda.current_stream(x.device).cuda_stream
-    _cabi.check(lib.wfk_stage_vil_u8(x.data_ptr(), n, h, w, t, out.data_ptr(), 0 if dtype == torch.float32 else 1,
-                                     stream), "wfk_stage_vil_u8")
+    with engine.timed_pass("stage_vil", float(x.numel()) * (1 + out.element_size())):
+        _cabi.check(lib.wfk_stage_vil_u8(x.data_ptr(), n, h, w, t, out.data_ptr(), 0 if dtype == torch.float32 else 1,
+                                         stream), "wfk_stage_vil_u8")
     return out
 
 
@@ -107,9 +108,11 @@ class LatentLinearPredictor(nn.Linear):
         tgt = torch.empty_like(pred)
         loss = torch.zeros(2, dtype=torch.float64, device=v.device)
         stream = torch.cuda.current_stream(v.device).cuda_stream
-        _cabi.check(lib.wfk_predict_linear(v.data_ptr(), wt.data_ptr(), bs.data_ptr(), b, self.input_frames,
-                                           self.pred_frames, c, h * w, pred.data_ptr(), tgt.data_ptr(),
-                                           loss.data_ptr(), stream), "wfk_predict_linear")
+        # algorithmic traffic: the 13 + 12 latent frames read once, 12 predicted frames written
+        with engine.timed_pass("predict_linear", 4.0 * (v.numel() + pred.numel())):
+            _cabi.check(lib.wfk_predict_linear(v.data_ptr(), wt.data_ptr(), bs.data_ptr(), b, self.input_frames,
+                                               self.pred_frames, c, h * w, pred.data_ptr(), tgt.data_ptr(),
+                                               loss.data_ptr(), stream), "wfk_predict_linear")
         return pred, tgt, (loss[0] / loss[1]).to(torch.float32)
 
 
@@ -153,8 +156,11 @@ class Autoencoder(nn.Module):
     def decode(self, x: torch.Tensor) -> torch.Tensor:
         b, t, c, h, w = x.shape
         flat = x.reshape(b * t, c, h, w)
-        outs = [self.autoencoder.decode(flat[i:i + self.frames_per_call]) for i in range(0, b * t, self.frames_per_call)]
-        y = torch.cat(outs, dim=0)
+        ae = self.autoencoder
+        nb = len(ae._cfg["block_out_channels"]) - 1
+        y = torch.empty((b * t, ae._cfg["out_channels"], h << nb, w << nb), dtype=torch.float32, device=x.device)
+        for i in range(0, b * t, self.frames_per_call):   # each chunk lands in its slice of the result
+            ae.decode_into(flat[i:i + self.frames_per_call], y[i:i + self.frames_per_call])
         return y.reshape(b, t, *y.shape[1:])
 
 
