@@ -52,7 +52,7 @@ class Harness(_Program):
     def go(self):
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.stats_arena.zero_()
-        for fn, args, what, _ in self.ops:
+        for fn, args, what, *_ in self.ops:
             _cabi.check(fn(*args, stream), what)
         torch.cuda.synchronize()
 

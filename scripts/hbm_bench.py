@@ -67,7 +67,16 @@ def main():
         pred.weight.data.copy_(w)
         pred.bias.data.copy_(b)
         lat = torch.randn(B, 25, 4, 48, 48, device=dev)
-        timeit("predict_linear 52->48", lambda: pred.rollout(lat), 921600.0 * B)
+        lib = _cabi.load()
+        po, to = torch.empty(B, 12, 4, 48, 48, device=dev), torch.empty(B, 12, 4, 48, 48, device=dev)
+        ls = torch.zeros(2, dtype=torch.float64, device=dev)
+        wt, bs = pred.weight.detach().contiguous(), pred.bias.detach().contiguous()
+        st = torch.cuda.current_stream().cuda_stream
+        # the C call alone (rollout() adds a zero-fill and two scalar kernels around it)
+        timeit("predict_linear 52->48", lambda: _cabi.check(lib.wfk_predict_linear(
+            lat.data_ptr(), wt.data_ptr(), bs.data_ptr(), B, 13, 12, 4, 48 * 48, po.data_ptr(), to.data_ptr(), ls.data_ptr(), st)),
+            921600.0 * B)
+        timeit("predictor.rollout (API)", lambda: pred.rollout(lat), 921600.0 * B)
     if args.only in (None, "metrics"):
         torch.manual_seed(0)
         u8 = make_vil_sequences(2, H, W, 13, seed=31).to(dev)
@@ -76,7 +85,17 @@ def main():
         pr = x[:, :12].repeat(reps, 1, 1, 1, 1)[: B * 12 // 12].contiguous() if False else x[:, :12].repeat(reps, 1, 1, 1, 1).reshape(-1, 1, H, W)[: B * 12].contiguous()
         tg = x[:, 1:13].repeat(reps, 1, 1, 1, 1).reshape(-1, 1, H, W)[: B * 12].contiguous()
         pr = (pr + 0.02 * torch.randn_like(pr)).contiguous()
-        timeit(f"metrics {B * 12} frame pairs", lambda: M.metric_partials_device(pr, tg), 8.0 * pr.numel())
+        import ctypes as C
+        lib = _cabi.load()
+        nf = pr.shape[0]
+        ws_bytes = lib.wfk_metrics_workspace_bytes(nf, H, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        outp = torch.empty(108, dtype=torch.int64, device=dev)
+        thr = (C.c_float * 6)(*[float(torch.tensor(v, dtype=torch.float32)) for v in M.THRESHOLDS])
+        st = torch.cuda.current_stream().cuda_stream
+        timeit(f"wfk_metrics {nf} frame pairs", lambda: _cabi.check(lib.wfk_metrics(
+            pr.data_ptr(), tg.data_ptr(), nf, H, W, thr, 6, 1, outp.data_ptr(), ws.data_ptr(), ws_bytes, st)), 8.0 * pr.numel())
+        timeit("metric_partials_device (API)", lambda: M.metric_partials_device(pr, tg), 8.0 * pr.numel())
     if args.out:
         with open(args.out, "w") as f:
             json.dump(res, f, indent=1)

@@ -53,7 +53,7 @@ def _go(h):
     from weatherforecastingtoolkit_b200 import _cabi
     stream = torch.cuda.current_stream().cuda_stream
     h.stats_arena.zero_()
-    for fn, args, what, _ in h.ops:
+    for fn, args, what, *_ in h.ops:
         _cabi.check(fn(*args, stream), what)
     torch.cuda.synchronize()
 
@@ -129,7 +129,7 @@ def test_groupnorm_silu(engine):
         stream = torch.cuda.current_stream().cuda_stream
         st.copy_(_ref_stats(x.float(), 32))
         from weatherforecastingtoolkit_b200 import _cabi
-        for fn, args, what, _ in hs.ops:
+        for fn, args, what, *_ in hs.ops:
             _cabi.check(fn(*args, stream), what)
         torch.cuda.synchronize()
         ref = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-6)

@@ -137,6 +137,16 @@ def test_metrics_ragged_and_wide_shapes(lib, shape):
     assert mp.sq_sum == pytest.approx(want["sq_sum"], rel=1e-5)
 
 
+def test_metrics_unsorted_thresholds(lib):
+    """The kernel sorts thresholds internally (early exit of its compare loop); counts come back in the caller's order."""
+    from oracle import metrics_oracle as MO
+    from weatherforecastingtoolkit_b200 import metrics as M
+    p, t = metric_case_inputs("vil_2x12x384")
+    thr = [0.6, 16 / 255, 0.4, 219 / 255, 0.05]
+    mp = M.metric_partials(p[:1, :4].to(DEV), t[:1, :4].to(DEV), thr)
+    assert mp.counts.tolist() == MO.integer_counts(p[:1, :4], t[:1, :4], thr).tolist()
+
+
 def test_log_metrics_gpu(lib):
     """rollout.log_metrics == pipeline.helpers.log_metrics (helpers.py:142-153): tag-prefixed calc_metrics dict handed
     to pl_module.log_dict(on_step=True, on_epoch=True, sync_dist=True)."""

@@ -12,21 +12,26 @@
 // Bit-exactness of the pooled counts: F.avg_pool2d sums a window sequentially in row-major order in
 // fp32 and divides by k*k; the pooling lanes reproduce exactly that association order.
 //
-// Work decomposition (v2). The pass is nominally HBM-bound (8 B per pixel pair) but the 11x11 window costs
-// 2 x 11 taps x 4 maps = 88 FMAs per pixel, so the kernel is built around the fp32 pipe:
-//   * one CTA = one 32-row segment of one column strip of one frame, `nwc` column warps + 1 pool warp;
-//   * a column thread owns TWO adjacent columns and walks the segment in chunks of 8 output rows:
+// Work decomposition (v3). The pass is nominally HBM-bound (8 B per pixel pair) but the 11x11 window costs
+// 2 x 11 taps x 4 maps = 88 FMAs per pixel, so the kernel is built around the fp32 pipe (measured on B200,
+// scripts/probes/fp32_rate.cu: 97 FFMA lanes/clk/SM, 64 FFMA2 lanes/clk/SM = 128 FMAs/clk/SM):
+//   * one CTA = one 32-row segment of one column strip of one frame, `nwc` warps of 64 columns;
+//   * a thread owns TWO adjacent columns and walks the segment in chunks of 8 output rows:
 //       V pass  -- 18 input rows come straight from global memory as 64-bit loads (256 B per warp and
-//                  row), are clamped, counted (ballot/popc) when they are the chunk's own rows, and are
-//                  pushed through the vertical 11-tap filter in registers with PACKED fp32x2 FMAs (the
-//                  pair = the thread's two columns): 4 maps (p, t, p*p + t*t, p*t) x 8 output rows;
-//                  the filtered rows go to shared memory as (mu_p, mu_t) / (E[pp+tt], E[pt]) pairs;
-//       H pass  -- tasks of 1 row x 8 columns read 18 columns of those pairs (128-bit loads, rows padded
-//                  so that the 8 rows of a task group hit 8 different bank groups) and apply the
-//                  horizontal taps again as packed FMAs (the pair = two maps), then the SSIM formula;
-//   * the pool warp is decoupled (reads global memory, never waits for the column warps): one lane per
-//     4x4 / 16x16 window runs the sequential fp32 chain F.avg_pool2d runs, so a 256-add chain occupies
-//     one lane of one warp instead of stalling a block.
+//                  row), are clamped and pushed through the vertical 11-tap filter in registers with
+//                  PACKED fp32x2 FMAs (the pair = the thread's two columns): 4 maps (p, t, p*p + t*t, p*t)
+//                  x 8 output rows; the filtered rows go to shared memory as (mu_p, mu_t) / (E[pp+tt],
+//                  E[pt]) pairs. The chunk's own 8 rows are also (a) counted against the thresholds as
+//                  per-thread BIT MASKS (one predicated OR per compare; 3 popc per threshold and chunk
+//                  instead of a ballot + popc per row: POPC issues at 1/8 rate), (b) written to shared memory
+//                  as (p, t) pairs for the pooling tasks;
+//       tasks   -- after one block barrier the warps pull warp-sized tasks from a shared queue:
+//                  * pool 16: one lane per 16x16 window continues the sequential fp32 chain F.avg_pool2d
+//                    runs (8 rows of it per chunk, the running sums carried in shared memory);
+//                  * pool 4: one lane per 4x4 window;
+//                  * H pass: 1 row x 16 columns per lane, 26 columns of the filtered pairs read with 128-bit
+//                    loads (rows padded so that the 8 rows of a lane group hit 8 different bank groups), the
+//                    horizontal taps again as packed FMAs (the pair = two maps), then the SSIM formula.
 // sigma_p^2 + sigma_t^2 enters SSIM only as a sum, so E[pp] and E[tt] are filtered as ONE map and the
 // variance clamp (torchmetrics >= 1.x clamps each variance at 0, older releases do not clamp) is
 // applied to the sum: the three variants differ by rounding-level amounts (< 1e-5 relative on pixels of
@@ -39,12 +44,13 @@ namespace wfk {
 
 constexpr int kHalo = 5;
 constexpr int kSegRows = 32;     // rows per CTA (multiple of 16: pooling windows never straddle CTAs)
-constexpr int kChunkRows = 8;    // output rows per V / H pass
+constexpr int kChunkRows = 8;    // output rows per V pass / task phase
 constexpr int kVRows = kChunkRows + 2 * kHalo;
 constexpr int kMaxColWarps = 6;  // 6 x 64 = 384 columns per strip (one strip for the 384-wide VIL frames)
-constexpr int kMetThreadsMax = 32 * (kMaxColWarps + 1);
-constexpr int kMetWarpsMax = kMaxColWarps + 1;
+constexpr int kMetThreadsMax = 32 * kMaxColWarps;
 constexpr int kSmemPadPx = 8;    // pad pixels in front of a filtered row (the H pass reads 5 to the left)
+constexpr int kHCols = 16;       // output columns per H-pass lane task
+constexpr int kWinBytes = 16 * 8 + 16;  // raw (p, t) pairs of one 16-pixel window row + 16 B skew (conflict-free pool-16 reads)
 
 struct MetricsParams {
   const float* pred;
@@ -52,12 +58,12 @@ struct MetricsParams {
   int h, w, frames;
   int nthr;
   int clamp01;
-  int nwc;    // column warps per CTA
+  int nwc;    // warps (64 columns each) per CTA
   int ns;     // column strips per frame
   int own;    // columns owned per strip when ns > 1 (64 * nwc - 32: 16 columns of overlap either side)
   int nseg;   // row segments per frame
   int vec2;   // 64-bit loads allowed (w even, base pointers 8-byte aligned)
-  int vec4;   // 128-bit loads allowed in the pool warp (w % 4 == 0, base pointers 16-byte aligned)
+  int perm[WFK_MAX_THRESHOLDS];  // thr[] is sorted ascending; perm[k] = position of thr[k] in the caller's list
   float thr[WFK_MAX_THRESHOLDS];
   float gauss[11];
   float c1, c2;
@@ -86,126 +92,43 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float clamp01f(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
 
-// Ballot/popc contingency update for one (pred, target) value per lane.
-__device__ __forceinline__ void count_thresholds(const MetricsParams& p, bool valid, float pv, float tv,
-                                                 int (&c)[WFK_MAX_THRESHOLDS][3]) {
+// Ballot/popc contingency update for one (pred, target) value per lane (pooled cells: a few warp tasks per chunk),
+// accumulated straight into the CTA's shared counters by lane 0.
+__device__ __forceinline__ void count_thresholds_smem(const MetricsParams& p, bool valid, float pv, float tv, int lane,
+                                                      int* s_cnt) {
 #pragma unroll
   for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) {
     if (k < p.nthr) {
       const unsigned bp = __ballot_sync(0xffffffffu, valid && (pv >= p.thr[k]));
       const unsigned bt = __ballot_sync(0xffffffffu, valid && (tv >= p.thr[k]));
-      c[k][0] += __popc(bp & bt);
-      c[k][1] += __popc(bp);
-      c[k][2] += __popc(bt);
-    }
-  }
-}
-// Same for the two pixels a column thread owns.
-__device__ __forceinline__ void count_thresholds2(const MetricsParams& p, bool v0, bool v1, const float2 pv,
-                                                  const float2 tv, int (&c)[WFK_MAX_THRESHOLDS][3]) {
-#pragma unroll
-  for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) {
-    if (k < p.nthr) {
-      const float th = p.thr[k];
-      const unsigned bp0 = __ballot_sync(0xffffffffu, v0 && (pv.x >= th));
-      const unsigned bt0 = __ballot_sync(0xffffffffu, v0 && (tv.x >= th));
-      const unsigned bp1 = __ballot_sync(0xffffffffu, v1 && (pv.y >= th));
-      const unsigned bt1 = __ballot_sync(0xffffffffu, v1 && (tv.y >= th));
-      c[k][0] += __popc(bp0 & bt0) + __popc(bp1 & bt1);
-      c[k][1] += __popc(bp0) + __popc(bp1);
-      c[k][2] += __popc(bt0) + __popc(bt1);
-    }
-  }
-}
-
-// The pool warp: one lane per K x K window owned by this CTA; sequential row-major fp32 sum, then * 1/K^2
-// (exact for powers of two) -- the association order of F.avg_pool2d.
-template <int K>
-__device__ __forceinline__ void pool_windows(const MetricsParams& p, const float* __restrict__ pf,
-                                             const float* __restrict__ tf, int y0, int y1, int own0, int own1, int lane,
-                                             int* s_counts, int* s_n, float& abs_acc) {
-  const int wy0 = y0 / K, wy1 = y1 / K, wx0 = own0 / K, wx1 = own1 / K;
-  const int nwx = max(wx1 - wx0, 0), nwy = max(wy1 - wy0, 0);
-  const int items = nwx * nwy;
-  int c[WFK_MAX_THRESHOLDS][3];
-#pragma unroll
-  for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) c[k][0] = c[k][1] = c[k][2] = 0;
-#pragma unroll 1
-  for (int base = 0; base < items; base += 32) {
-    const int i = base + lane;
-    const bool valid = i < items;
-    float sp = 0.f, st = 0.f;
-    if (valid) {
-      const int wy = wy0 + i / nwx, wx = wx0 + i % nwx;
-      const float* rp = pf + static_cast<int64_t>(wy * K) * p.w + wx * K;
-      const float* rt = tf + static_cast<int64_t>(wy * K) * p.w + wx * K;
-      if (p.vec4) {
-#pragma unroll 4
-        for (int rr = 0; rr < K; ++rr) {
-          float4 a[K / 4], b[K / 4];
-#pragma unroll
-          for (int q = 0; q < K / 4; ++q) {
-            a[q] = __ldg(reinterpret_cast<const float4*>(rp) + q);
-            b[q] = __ldg(reinterpret_cast<const float4*>(rt) + q);
-          }
-#pragma unroll
-          for (int q = 0; q < K / 4; ++q) {
-            if (p.clamp01) {
-              a[q] = make_float4(clamp01f(a[q].x), clamp01f(a[q].y), clamp01f(a[q].z), clamp01f(a[q].w));
-              b[q] = make_float4(clamp01f(b[q].x), clamp01f(b[q].y), clamp01f(b[q].z), clamp01f(b[q].w));
-            }
-            sp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sp, a[q].x), a[q].y), a[q].z), a[q].w);
-            st = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(st, b[q].x), b[q].y), b[q].z), b[q].w);
-          }
-          rp += p.w;
-          rt += p.w;
-        }
-      } else {
-#pragma unroll 1
-        for (int rr = 0; rr < K; ++rr) {
-#pragma unroll
-          for (int cc = 0; cc < K; ++cc) {
-            float a = __ldg(rp + cc), b = __ldg(rt + cc);
-            if (p.clamp01) {
-              a = clamp01f(a);
-              b = clamp01f(b);
-            }
-            sp = __fadd_rn(sp, a);
-            st = __fadd_rn(st, b);
-          }
-          rp += p.w;
-          rt += p.w;
-        }
+      if (lane == 0 && (bp | bt)) {
+        atomicAdd(&s_cnt[k * 3 + 0], __popc(bp & bt));
+        atomicAdd(&s_cnt[k * 3 + 1], __popc(bp));
+        atomicAdd(&s_cnt[k * 3 + 2], __popc(bt));
       }
-      sp = __fmul_rn(sp, 1.0f / (K * K));
-      st = __fmul_rn(st, 1.0f / (K * K));
-      abs_acc += fabsf(sp - st);
     }
-    count_thresholds(p, valid, sp, st, c);
-  }
-  if (lane == 0) {   // only this warp writes the pooled slots
-#pragma unroll
-    for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) {
-      s_counts[k * 3 + 0] = c[k][0];
-      s_counts[k * 3 + 1] = c[k][1];
-      s_counts[k * 3 + 2] = c[k][2];
-    }
-    *s_n = items;
   }
 }
 
+template <bool VEC2>
 __global__ void __launch_bounds__(kMetThreadsMax, 2) metrics_strip_kernel(const __grid_constant__ MetricsParams p,
                                                                          TileRec* __restrict__ recs) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwc = p.nwc;
-  const int ncol_thr = 32 * nwc;
+  const int nthreads = 32 * nwc;
   const int pitch = 64 * nwc + 2 * kSmemPadPx + 2;  // pixels; the +2 (16 B) skews consecutive rows across bank groups
+  const int rpitch = 4 * nwc * kWinBytes;           // bytes per raw row
   float2* VA = reinterpret_cast<float2*>(smem_raw);  // [kChunkRows][pitch] (mu_p, mu_t)
   float2* VB = VA + kChunkRows * pitch;              // [kChunkRows][pitch] (E[pp + tt], E[pt])
-  int* s_counts = reinterpret_cast<int*>(VB + kChunkRows * pitch);  // [pools][thresholds][3]
-  int* s_n = s_counts + WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3;     // [pools]
-  float* s_wred = reinterpret_cast<float*>(s_n + 4);                // [warps][8]
+  uint8_t* RAW = reinterpret_cast<uint8_t*>(VB + kChunkRows * pitch);   // [kChunkRows][4 nwc windows][144 B]
+  int* s_counts = reinterpret_cast<int*>(RAW + kChunkRows * rpitch);    // [pools][thresholds][3]
+  int* s_n = s_counts + WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3;         // [pools] (+ task counter in s_n[3])
+  float* s_carry = reinterpret_cast<float*>(s_n + 4);                   // [4 nwc windows][2] running pool-16 sums
+  float* s_wred = s_carry + 2 * 4 * kMaxColWarps;                       // [warps][8]
+  // Task results are accumulated per ITEM (an item is served by whichever warp pulls its task, so per-thread partials
+  // would group the floats differently from run to run): [H items 32 nwc | pool-4 items 32 nwc | pool-16 windows 32]
+  float* s_item = s_wred + 8 * kMaxColWarps;
 
   const int f = blockIdx.z, strip = blockIdx.x, seg = blockIdx.y;
   const int c0 = (p.ns == 1) ? 0 : strip * p.own - 16;
@@ -215,78 +138,96 @@ __global__ void __launch_bounds__(kMetThreadsMax, 2) metrics_strip_kernel(const 
   const float* __restrict__ pf = p.pred + static_cast<int64_t>(f) * p.h * p.w;
   const float* __restrict__ tf = p.tgt + static_cast<int64_t>(f) * p.h * p.w;
 
-  for (int i = tid; i < WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3 + 4; i += blockDim.x) s_counts[i] = 0;
+  for (int i = tid; i < WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3 + 4; i += nthreads) s_counts[i] = 0;
+  for (int i = tid; i < 64 * nwc + 32; i += nthreads) s_item[i] = 0.f;
   __syncthreads();
 
   float r_abs1 = 0.f, r_sq = 0.f, r_mx = -INFINITY, r_mn = INFINITY, r_ssim = 0.f, r_abs4 = 0.f, r_abs16 = 0.f;
+  int n4 = 0, n16 = 0;   // pooled cells counted by this lane
 
-  if (warp == nwc) {
-    // ------------------------------------------------------------------ pool warp
-    pool_windows<4>(p, pf, tf, y_lo, y_hi, own0, own1, lane, s_counts + 1 * WFK_MAX_THRESHOLDS * 3, s_n + 1, r_abs4);
-    pool_windows<16>(p, pf, tf, y_lo, y_hi, own0, own1, lane, s_counts + 2 * WFK_MAX_THRESHOLDS * 3, s_n + 2, r_abs16);
-  } else {
-    // ------------------------------------------------------------------ column warps
-    const int lc = 2 * tid;            // local column of this thread's pair
-    const int gc = c0 + lc;            // global column (may be < 0 or >= w: masked)
-    const bool in0 = gc >= 0 && gc < p.w, in1 = gc + 1 >= 0 && gc + 1 < p.w;
-    const bool vec = p.vec2 && in0 && in1;
-    const bool o0 = gc >= own0 && gc < own1, o1 = gc + 1 >= own0 && gc + 1 < own1;
-    float2 g2[6];
+  const int lc = 2 * tid;            // local column of this thread's pair
+  const int gc = c0 + lc;            // global column (may be < 0 or >= w: masked)
+  const bool in0 = gc >= 0 && gc < p.w, in1 = gc + 1 >= 0 && gc + 1 < p.w;
+  // clamped (always in-bounds, even) column for the branch-free loads; values of masked columns are zeroed afterwards
+  const int gcl = VEC2 ? min(max(gc, 0), p.w - 2) : min(max(gc, 0), p.w - 1);
+  const int gcl1 = min(max(gc + 1, 0), p.w - 1);
+  const bool o0 = gc >= own0 && gc < own1, o1 = gc + 1 >= own0 && gc + 1 < own1;
+  float2 g2[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) g2[k] = make_float2(p.gauss[k], p.gauss[k]);
-    int cnt[WFK_MAX_THRESHOLDS][3];
-#pragma unroll
-    for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) cnt[k][0] = cnt[k][1] = cnt[k][2] = 0;
-    const int x_lo = max(kHalo, own0), x_hi = min(p.w - kHalo, own1);  // SSIM centres this CTA scores
+  for (int k = 0; k < 6; ++k) g2[k] = make_float2(p.gauss[k], p.gauss[k]);
+  const int x_lo = max(kHalo, own0), x_hi = min(p.w - kHalo, own1);  // SSIM centres this CTA scores
+  uint8_t* raw_mine = RAW + (lc >> 4) * kWinBytes + (lc & 15) * 8;
 
 #pragma unroll 1
-    for (int y0 = y_lo; y0 < y_hi; y0 += kChunkRows) {
-      // ---- V pass: rows y0-5 .. y0+12 -> 8 vertically filtered rows of the 4 maps, in registers
-      float2 aP[kChunkRows], aT[kChunkRows], aS[kChunkRows], aX[kChunkRows];
+  for (int y0 = y_lo; y0 < y_hi; y0 += kChunkRows) {
+    // ---- V pass: rows y0-5 .. y0+12 -> 8 vertically filtered rows of the 4 maps, in registers
+    float2 aP[kChunkRows], aT[kChunkRows], aS[kChunkRows], aX[kChunkRows];
 #pragma unroll
-      for (int j = 0; j < kChunkRows; ++j) aP[j] = aT[j] = aS[j] = aX[j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < kChunkRows; ++j) aP[j] = aT[j] = aS[j] = aX[j] = make_float2(0.f, 0.f);
+    unsigned mp[WFK_MAX_THRESHOLDS], mt[WFK_MAX_THRESHOLDS];   // bit 2j + e: (row j, column e) >= threshold
 #pragma unroll
-      for (int dy = 0; dy < kVRows; ++dy) {
+    for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) mp[k] = mt[k] = 0u;
+    if (tid == 0) s_n[3] = 0;   // task queue of this chunk (read after the barrier below)
+    // Loads are issued in batches of 6 rows, two batches in flight (branch-free: clamped addresses, out-of-image
+    // values zeroed afterwards). Loading a row right where it is consumed made every row pay a full global-memory
+    // round trip: the V pass was latency-bound at 1/4 of its instruction-issue time.
+    constexpr int kBatch = 6;
+    float2 bp[2][kBatch], bt[2][kBatch];
+    auto load_batch = [&](const int b0, float2 (&dp)[kBatch], float2 (&dt)[kBatch]) {
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        // 32-bit element offsets inside the frame (h * w < 2^31); rows clamped into the image
+        const int y = min(max(y0 - kHalo + b0 + i, 0), p.h - 1);
+        const unsigned row = static_cast<unsigned>(y) * static_cast<unsigned>(p.w);
+        if (VEC2) {
+          dp[i] = __ldg(reinterpret_cast<const float2*>(pf + (row + gcl)));
+          dt[i] = __ldg(reinterpret_cast<const float2*>(tf + (row + gcl)));
+        } else {
+          dp[i] = make_float2(__ldg(pf + (row + gcl)), __ldg(pf + (row + gcl1)));
+          dt[i] = make_float2(__ldg(tf + (row + gcl)), __ldg(tf + (row + gcl1)));
+        }
+      }
+    };
+    auto compute_batch = [&](const int b0, const float2 (&sp)[kBatch], const float2 (&st)[kBatch]) {
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const int dy = b0 + i;
         const int y = y0 - kHalo + dy;
-        float2 pv = make_float2(0.f, 0.f), tv = make_float2(0.f, 0.f);
-        if (y >= 0 && y < p.h) {
-          const int64_t o = static_cast<int64_t>(y) * p.w + gc;
-          if (vec) {
-            pv = __ldg(reinterpret_cast<const float2*>(pf + o));
-            tv = __ldg(reinterpret_cast<const float2*>(tf + o));
-          } else {
-            if (in0) {
-              pv.x = __ldg(pf + o);
-              tv.x = __ldg(tf + o);
-            }
-            if (in1) {
-              pv.y = __ldg(pf + o + 1);
-              tv.y = __ldg(tf + o + 1);
-            }
-          }
-          if (p.clamp01) {
-            pv = make_float2(clamp01f(pv.x), clamp01f(pv.y));
-            tv = make_float2(clamp01f(tv.x), clamp01f(tv.y));
-          }
+        // Rows / columns outside the image carry the clamped-address values of the border: they only ever reach
+        // SSIM centres and pooling windows that are not scored, and the pool-1 statistics below mask them explicitly.
+        float2 pv = sp[i], tv = st[i];
+        if (p.clamp01) {
+          pv = make_float2(clamp01f(pv.x), clamp01f(pv.y));
+          tv = make_float2(clamp01f(tv.x), clamp01f(tv.y));
         }
         if (dy >= kHalo && dy < kHalo + kChunkRows) {
-          // the chunk's own rows: pool-1 contingency counts, |d|, d^2, max / min(target)
+          // the chunk's own rows: raw pairs for the pooling tasks, pool-1 contingency masks, |d|, d^2, max / min(target)
+          const int j = dy - kHalo;
+          *reinterpret_cast<float4*>(raw_mine + j * rpitch) = make_float4(pv.x, tv.x, pv.y, tv.y);
           const bool rowok = y < p.h;
           const bool v0 = rowok && o0, v1 = rowok && o1;
           const float dx = pv.x - tv.x, dyv = pv.y - tv.y;
-          if (v0) {
-            r_abs1 += fabsf(dx);
-            r_sq = fmaf(dx, dx, r_sq);
-            r_mx = fmaxf(r_mx, tv.x);
-            r_mn = fminf(r_mn, tv.x);
+          r_abs1 += (v0 ? fabsf(dx) : 0.f) + (v1 ? fabsf(dyv) : 0.f);
+          r_sq = fmaf(v0 ? dx : 0.f, dx, r_sq);
+          r_sq = fmaf(v1 ? dyv : 0.f, dyv, r_sq);
+          // invalid pixels compare as -inf (and as +inf for the minimum)
+          const float c_px = v0 ? pv.x : -INFINITY, c_py = v1 ? pv.y : -INFINITY;
+          const float c_tx = v0 ? tv.x : -INFINITY, c_ty = v1 ? tv.y : -INFINITY;
+          r_mx = fmaxf(r_mx, fmaxf(c_tx, c_ty));
+          r_mn = fminf(r_mn, fminf(v0 ? tv.x : INFINITY, v1 ? tv.y : INFINITY));
+          // thresholds are ascending (sorted by the host wrapper): once no pixel of the warp's 64 reaches threshold k,
+          // none reaches a later one -- VIL fields are mostly below the first threshold
+          const float c_max = fmaxf(fmaxf(c_px, c_py), fmaxf(c_tx, c_ty));
+#pragma unroll
+          for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) {
+            if (k >= p.nthr) break;
+            const float th = p.thr[k];
+            if (!__any_sync(0xffffffffu, c_max >= th)) break;
+            if (c_px >= th) mp[k] |= 1u << (2 * j);
+            if (c_py >= th) mp[k] |= 1u << (2 * j + 1);
+            if (c_tx >= th) mt[k] |= 1u << (2 * j);
+            if (c_ty >= th) mt[k] |= 1u << (2 * j + 1);
           }
-          if (v1) {
-            r_abs1 += fabsf(dyv);
-            r_sq = fmaf(dyv, dyv, r_sq);
-            r_mx = fmaxf(r_mx, tv.y);
-            r_mn = fminf(r_mn, tv.y);
-          }
-          count_thresholds2(p, v0, v1, pv, tv, cnt);
         }
         const float2 ss = __ffma2_rn(tv, tv, __fmul2_rn(pv, pv));
         const float2 px = __fmul2_rn(pv, tv);
@@ -302,86 +243,174 @@ __global__ void __launch_bounds__(kMetThreadsMax, 2) metrics_strip_kernel(const 
           }
         }
       }
+    };
+    static_assert(kVRows == 3 * kBatch, "three batches of rows per chunk");
+    load_batch(0, bp[0], bt[0]);
+    load_batch(kBatch, bp[1], bt[1]);
+    compute_batch(0, bp[0], bt[0]);
+    load_batch(2 * kBatch, bp[0], bt[0]);
+    compute_batch(kBatch, bp[1], bt[1]);
+    compute_batch(2 * kBatch, bp[0], bt[0]);
 #pragma unroll
-      for (int j = 0; j < kChunkRows; ++j) {
-        const int si = j * pitch + kSmemPadPx + lc;
-        *reinterpret_cast<float4*>(VA + si) = make_float4(aP[j].x, aT[j].x, aP[j].y, aT[j].y);
-        *reinterpret_cast<float4*>(VB + si) = make_float4(aS[j].x, aX[j].x, aS[j].y, aX[j].y);
+    for (int j = 0; j < kChunkRows; ++j) {
+      const int si = j * pitch + kSmemPadPx + lc;
+      *reinterpret_cast<float4*>(VA + si) = make_float4(aP[j].x, aT[j].x, aP[j].y, aT[j].y);
+      *reinterpret_cast<float4*>(VB + si) = make_float4(aS[j].x, aX[j].x, aS[j].y, aX[j].y);
+    }
+    // pool-1 counts of the chunk: 3 popc + 3 warp-wide integer reductions per threshold
+#pragma unroll
+    for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) {
+      if (k < p.nthr) {
+        const unsigned any = __reduce_or_sync(0xffffffffu, mp[k] | mt[k]);
+        if (any) {
+          const int c_pt = __reduce_add_sync(0xffffffffu, __popc(mp[k] & mt[k]));
+          const int c_p = __reduce_add_sync(0xffffffffu, __popc(mp[k]));
+          const int c_t = __reduce_add_sync(0xffffffffu, __popc(mt[k]));
+          if (lane == 0) {
+            atomicAdd(&s_counts[k * 3 + 0], c_pt);
+            atomicAdd(&s_counts[k * 3 + 1], c_p);
+            atomicAdd(&s_counts[k * 3 + 2], c_t);
+          }
+        }
       }
-      asm volatile("bar.sync 1, %0;" ::"r"(ncol_thr) : "memory");
-      // ---- H pass + SSIM: tasks of 1 row x 8 columns (consecutive lanes take consecutive ROWS: conflict-free)
-#pragma unroll 1
-      for (int task = tid; task < kChunkRows * 8 * nwc; task += ncol_thr) {
-        const int j = task & (kChunkRows - 1), kgrp = task >> 3;
+    }
+    __syncthreads();
+    // ---- task phase: warp-sized tasks from a shared queue: [pool 16] [H pass x nwc] [pool 4 x nwc]
+    const int n_tasks = 1 + 2 * nwc;
+    for (;;) {
+      int task = 0;
+      if (lane == 0) task = atomicAdd(&s_n[3], 1);
+      task = __shfl_sync(0xffffffffu, task, 0);
+      if (task >= n_tasks) break;
+      if (task == 0) {
+        // ---- pool 16: lane = window column; 8 more rows of the sequential row-major fp32 sum (F.avg_pool2d's order)
+        const int gx0 = c0 + 16 * lane;
+        const bool win = lane < 4 * nwc && gx0 >= own0 && gx0 < own1 && gx0 + 16 <= p.w && (y0 & ~15) + 16 <= p.h;
+        const bool second = ((y0 - y_lo) >> 3) & 1;
+        float sp = 0.f, st = 0.f;
+        if (win) {
+          if (second) {
+            sp = s_carry[2 * lane];
+            st = s_carry[2 * lane + 1];
+          }
+          const uint8_t* wr = RAW + lane * kWinBytes;
+#pragma unroll 2
+          for (int r = 0; r < kChunkRows; ++r) {
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(wr + r * rpitch + 16 * q);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              sp = __fadd_rn(__fadd_rn(sp, v[q].x), v[q].z);
+              st = __fadd_rn(__fadd_rn(st, v[q].y), v[q].w);
+            }
+          }
+          if (!second) {
+            s_carry[2 * lane] = sp;
+            s_carry[2 * lane + 1] = st;
+          } else {
+            sp = __fmul_rn(sp, 1.0f / 256.0f);
+            st = __fmul_rn(st, 1.0f / 256.0f);
+            s_item[64 * nwc + lane] += fabsf(sp - st);
+            ++n16;
+          }
+        }
+        if (second) count_thresholds_smem(p, win, sp, st, lane, s_counts + 2 * WFK_MAX_THRESHOLDS * 3);
+      } else if (task <= nwc) {
+        // ---- H pass + SSIM: lane = (row j, 16-column group); consecutive lanes take consecutive ROWS (conflict-free)
+        const int item = (task - 1) * 32 + lane;
+        const int j = item & (kChunkRows - 1), kgrp = item >> 3;
         const int y = y0 + j;
-        const int gx0 = c0 + 8 * kgrp;
-        if (y < kHalo || y >= p.h - kHalo || gx0 >= x_hi || gx0 + 8 <= x_lo) continue;
-        float2 hA[8], hB[8];
+        const int gx0 = c0 + kHCols * kgrp;
+        if (y >= kHalo && y < p.h - kHalo && gx0 < x_hi && gx0 + kHCols > x_lo) {
+          float2 hA[kHCols], hB[kHCols];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) hA[o] = hB[o] = make_float2(0.f, 0.f);
-        const float2* ra = VA + j * pitch + kSmemPadPx + 8 * kgrp - kHalo;  // input column i = output column o + tap - 5
-        const float2* rb = VB + j * pitch + kSmemPadPx + 8 * kgrp - kHalo;
+          for (int o = 0; o < kHCols; ++o) hA[o] = hB[o] = make_float2(0.f, 0.f);
+          const float2* ra = VA + j * pitch + kSmemPadPx + kHCols * kgrp - kHalo;  // input column i = output column o + tap - 5
+          const float2* rb = VB + j * pitch + kSmemPadPx + kHCols * kgrp - kHalo;
+          // input columns 0 .. 25: 0 and 25 alone (64-bit), (1,2) (3,4) ... (23,24) as aligned pairs (128-bit)
 #pragma unroll
-        for (int i = 0; i < 8 + 2 * kHalo; ++i) {
-          // columns 1..16 come in aligned pairs (128-bit), the first and the last alone (64-bit)
-          float2 a, b;
-          if (i == 0 || i == 17) {
-            a = ra[i];
-            b = rb[i];
-          } else if (i & 1) {
-            const float4 a4 = *reinterpret_cast<const float4*>(ra + i);
-            const float4 b4 = *reinterpret_cast<const float4*>(rb + i);
-            a = make_float2(a4.x, a4.y);
-            b = make_float2(b4.x, b4.y);
+          for (int i = 0; i < kHCols + 2 * kHalo; ++i) {
+            float2 a, b, a_n = make_float2(0.f, 0.f), b_n = make_float2(0.f, 0.f);
+            bool pair = false;
+            if (i == 0 || i == kHCols + 2 * kHalo - 1) {
+              a = ra[i];
+              b = rb[i];
+            } else if (i & 1) {
+              const float4 a4 = *reinterpret_cast<const float4*>(ra + i);
+              const float4 b4 = *reinterpret_cast<const float4*>(rb + i);
+              a = make_float2(a4.x, a4.y);
+              b = make_float2(b4.x, b4.y);
+              a_n = make_float2(a4.z, a4.w);
+              b_n = make_float2(b4.z, b4.w);
+              pair = true;
+            } else {
+              continue;  // even i in 2 .. 24: consumed with its odd predecessor
+            }
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {   // the odd partner (column i + 1) is consumed here too
-              const int k = i + 1 - o;
+            for (int o = 0; o < kHCols; ++o) {
+              const int k = i - o;
               if (k >= 0 && k <= 2 * kHalo) {
                 const float2 g = g2[k <= kHalo ? k : 2 * kHalo - k];
-                hA[o] = __ffma2_rn(g, make_float2(a4.z, a4.w), hA[o]);
-                hB[o] = __ffma2_rn(g, make_float2(b4.z, b4.w), hB[o]);
+                hA[o] = __ffma2_rn(g, a, hA[o]);
+                hB[o] = __ffma2_rn(g, b, hB[o]);
+              }
+              const int k2 = i + 1 - o;
+              if (pair && k2 >= 0 && k2 <= 2 * kHalo) {
+                const float2 g = g2[k2 <= kHalo ? k2 : 2 * kHalo - k2];
+                hA[o] = __ffma2_rn(g, a_n, hA[o]);
+                hB[o] = __ffma2_rn(g, b_n, hB[o]);
               }
             }
-          } else {
-            continue;  // even i in 2..16: handled with its odd predecessor
           }
+          float acc = 0.f;
 #pragma unroll
-          for (int o = 0; o < 8; ++o) {
-            const int k = i - o;
-            if (k >= 0 && k <= 2 * kHalo) {
-              const float2 g = g2[k <= kHalo ? k : 2 * kHalo - k];
-              hA[o] = __ffma2_rn(g, a, hA[o]);
-              hB[o] = __ffma2_rn(g, b, hB[o]);
-            }
+          for (int o = 0; o < kHCols; ++o) {
+            const int gx = gx0 + o;
+            const float mu_p = hA[o].x, mu_t = hA[o].y;
+            const float mu_pp = mu_p * mu_p, mu_tt = mu_t * mu_t, mu_pt = mu_p * mu_t;
+            const float sig_sum = fmaxf((hB[o].x - mu_pp) - mu_tt, 0.f);
+            const float sig_pt = hB[o].y - mu_pt;
+            const float upper = 2.f * sig_pt + p.c2;
+            const float lower = sig_sum + p.c2;
+            const float val = __fdividef((2.f * mu_pt + p.c1) * upper, (mu_pp + mu_tt + p.c1) * lower);
+            acc += (gx >= x_lo && gx < x_hi) ? val : 0.f;
           }
+          s_item[item] += acc;
         }
+      } else {
+        // ---- pool 4: lane = one 4x4 window of the chunk's two window rows
+        const int item = (task - 1 - nwc) * 32 + lane;
+        const int per_row = 16 * nwc;
+        const int wrow = item / per_row, w4 = item - wrow * per_row;
+        const int lx = 4 * w4, gx0 = c0 + lx;
+        const bool win = wrow < 2 && gx0 >= own0 && gx0 < own1 && gx0 + 4 <= p.w && y0 + 4 * wrow + 4 <= p.h;
+        float sp = 0.f, st = 0.f;
+        if (win) {
+          const uint8_t* wr = RAW + (4 * wrow) * rpitch + (lx >> 4) * kWinBytes + (lx & 15) * 8;
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          const int gx = gx0 + o;
-          const float mu_p = hA[o].x, mu_t = hA[o].y;
-          const float mu_pp = mu_p * mu_p, mu_tt = mu_t * mu_t, mu_pt = mu_p * mu_t;
-          const float sig_sum = fmaxf((hB[o].x - mu_pp) - mu_tt, 0.f);
-          const float sig_pt = hB[o].y - mu_pt;
-          const float upper = 2.f * sig_pt + p.c2;
-          const float lower = sig_sum + p.c2;
-          const float val = __fdividef((2.f * mu_pt + p.c1) * upper, (mu_pp + mu_tt + p.c1) * lower);
-          r_ssim += (gx >= x_lo && gx < x_hi) ? val : 0.f;
+          for (int r = 0; r < 4; ++r) {
+            const float4 v0 = *reinterpret_cast<const float4*>(wr + r * rpitch);
+            const float4 v1 = *reinterpret_cast<const float4*>(wr + r * rpitch + 16);
+            sp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sp, v0.x), v0.z), v1.x), v1.z);
+            st = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(st, v0.y), v0.w), v1.y), v1.w);
+          }
+          sp = __fmul_rn(sp, 1.0f / 16.0f);
+          st = __fmul_rn(st, 1.0f / 16.0f);
+          s_item[32 * nwc + item] += fabsf(sp - st);
+          ++n4;
         }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(ncol_thr) : "memory");   // the next chunk overwrites VA / VB
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) {
-        if (k < p.nthr) {
-          atomicAdd(&s_counts[k * 3 + 0], cnt[k][0]);
-          atomicAdd(&s_counts[k * 3 + 1], cnt[k][1]);
-          atomicAdd(&s_counts[k * 3 + 2], cnt[k][2]);
-        }
+        count_thresholds_smem(p, win, sp, st, lane, s_counts + 1 * WFK_MAX_THRESHOLDS * 3);
       }
     }
+    __syncthreads();   // the next chunk overwrites VA / VB / RAW and resets the queue
   }
-  // ---- deterministic block reduction of the float partials
+  // ---- deterministic block reduction of the float partials (items: thread i folds items i, i + nthreads, ...)
+  for (int i = tid; i < 32 * nwc; i += nthreads) {
+    r_ssim += s_item[i];
+    r_abs4 += s_item[32 * nwc + i];
+  }
+  if (tid < 32) r_abs16 += s_item[64 * nwc + tid];
   r_abs1 = warp_sum(r_abs1);
   r_sq = warp_sum(r_sq);
   r_mx = warp_max(r_mx);
@@ -389,6 +418,8 @@ __global__ void __launch_bounds__(kMetThreadsMax, 2) metrics_strip_kernel(const 
   r_ssim = warp_sum(r_ssim);
   r_abs4 = warp_sum(r_abs4);
   r_abs16 = warp_sum(r_abs16);
+  n4 = __reduce_add_sync(0xffffffffu, n4);
+  n16 = __reduce_add_sync(0xffffffffu, n16);
   if (lane == 0) {
     float* d = s_wred + warp * 8;
     d[0] = r_abs1;
@@ -398,17 +429,19 @@ __global__ void __launch_bounds__(kMetThreadsMax, 2) metrics_strip_kernel(const 
     d[4] = r_abs4;
     d[5] = r_abs16;
     d[6] = r_mn;
+    atomicAdd(&s_n[1], n4);
+    atomicAdd(&s_n[2], n16);
   }
   __syncthreads();
   TileRec* rec = recs + (static_cast<int64_t>(f) * p.nseg + seg) * p.ns + strip;
-  for (int i = tid; i < WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3; i += blockDim.x) (&rec->counts[0][0][0])[i] = s_counts[i];
+  for (int i = tid; i < WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3; i += nthreads) (&rec->counts[0][0][0])[i] = s_counts[i];
   if (tid == 0) {
     rec->n[0] = max(y_hi - y_lo, 0) * max(own1 - own0, 0);
     rec->n[1] = s_n[1];
     rec->n[2] = s_n[2];
     float r[6] = {0.f, 0.f, -INFINITY, 0.f, 0.f, 0.f};
     float mnr = INFINITY;
-    for (int wi = 0; wi <= nwc; ++wi) {
+    for (int wi = 0; wi < nwc; ++wi) {
       const float* d = s_wred + wi * 8;
       r[0] += d[0];
       r[1] += d[1];
@@ -446,6 +479,7 @@ __global__ void __launch_bounds__(128) metrics_frame_kernel(const TileRec* __res
   FrameRec* out = frames_out + f;
   if (tid < kNumInt) {
     long long acc = 0;
+#pragma unroll 4
     for (int t = 0; t < tiles_per_frame; ++t) {
       const int* ip = (tid < kNumInt - WFK_NUM_POOLS) ? (&fr[t].counts[0][0][0] + tid) : (&fr[t].n[0] + (tid - (kNumInt - WFK_NUM_POOLS)));
       acc += *ip;
@@ -454,6 +488,7 @@ __global__ void __launch_bounds__(128) metrics_frame_kernel(const TileRec* __res
   } else if (tid >= 96 && tid < 96 + 7) {
     const int j = tid - 96;  // abs1, abs4, abs16, sq, ssim, max, min
     double acc = (j == 5) ? -INFINITY : ((j == 6) ? INFINITY : 0.0);
+#pragma unroll 4
     for (int t = 0; t < tiles_per_frame; ++t) {
       const TileRec& r = fr[t];
       const float v = j == 0 ? r.abs_sum[0] : j == 1 ? r.abs_sum[1] : j == 2 ? r.abs_sum[2] : j == 3 ? r.sq_sum
@@ -477,22 +512,36 @@ __global__ void __launch_bounds__(128) metrics_frame_kernel(const TileRec* __res
   }
 }
 
-__global__ void __launch_bounds__(128) metrics_finalize_kernel(const FrameRec* __restrict__ fr, int frames, int nthr,
-                                                               wfk_metric_partials* __restrict__ out) {
+// One block of 32 warps; output o (75 integer words + 6 doubles) belongs to warp o % 32. A lane sums frames
+// lane, lane + 32, ... in order and the warp folds the 32 partials with a fixed shuffle tree: deterministic, and 12
+// loads per lane instead of a serial chain of `frames` dependent L2 round trips in one thread (~0.4 us each).
+struct ThrPerm {
+  int v[WFK_MAX_THRESHOLDS];
+};
+__global__ void __launch_bounds__(1024) metrics_finalize_kernel(const FrameRec* __restrict__ fr, int frames, int nthr,
+                                                                const ThrPerm perm, wfk_metric_partials* __restrict__ out) {
   __shared__ long long s_i[kNumInt];
   __shared__ double s_d[6];
-  const int tid = threadIdx.x;
-  if (tid < kNumInt) {
-    long long acc = 0;
-    for (int f = 0; f < frames; ++f) acc += fr[f].ints[tid];
-    s_i[tid] = acc;
-  } else if (tid >= 96 && tid < 102) {
-    double acc = 0.0;
-    for (int f = 0; f < frames; ++f) acc += fr[f].f[tid - 96];
-    s_d[tid - 96] = acc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = warp; o < kNumInt + 6; o += 32) {
+    if (o < kNumInt) {
+      long long acc = 0;
+#pragma unroll 4
+      for (int f = lane; f < frames; f += 32) acc += fr[f].ints[o];
+#pragma unroll
+      for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) s_i[o] = acc;
+    } else {
+      double acc = 0.0;
+#pragma unroll 4
+      for (int f = lane; f < frames; f += 32) acc += fr[f].f[o - kNumInt];
+#pragma unroll
+      for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) s_d[o - kNumInt] = acc;
+    }
   }
   __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     for (int pl = 0; pl < WFK_NUM_POOLS; ++pl) {
       const long long n = s_i[kNumInt - WFK_NUM_POOLS + pl];
       for (int k = 0; k < WFK_MAX_THRESHOLDS; ++k) {
@@ -500,10 +549,11 @@ __global__ void __launch_bounds__(128) metrics_finalize_kernel(const FrameRec* _
         const long long c_p = s_i[(pl * WFK_MAX_THRESHOLDS + k) * 3 + 1];
         const long long c_t = s_i[(pl * WFK_MAX_THRESHOLDS + k) * 3 + 2];
         const bool on = k < nthr;
-        out->counts[pl][k][0] = on ? c_pt : 0;                 // tp
-        out->counts[pl][k][1] = on ? c_t - c_pt : 0;           // fn  (target yes, pred no)
-        out->counts[pl][k][2] = on ? c_p - c_pt : 0;           // fp  (pred yes, target no)
-        out->counts[pl][k][3] = on ? n - c_p - c_t + c_pt : 0; // tn
+        const int ko = on ? perm.v[k] : k;                      // position in the caller's threshold list
+        out->counts[pl][ko][0] = on ? c_pt : 0;                 // tp
+        out->counts[pl][ko][1] = on ? c_t - c_pt : 0;           // fn  (target yes, pred no)
+        out->counts[pl][ko][2] = on ? c_p - c_pt : 0;           // fp  (pred yes, target no)
+        out->counts[pl][ko][3] = on ? n - c_p - c_t + c_pt : 0; // tn
       }
       out->n_elems[pl] = n;
       out->abs_sum[pl] = s_d[pl];
@@ -538,8 +588,9 @@ static MetricsGeom metrics_geom(int h, int w) {
   }
   g.nseg = (h + kSegRows - 1) / kSegRows;
   const size_t pitch = static_cast<size_t>(64 * g.nwc + 2 * kSmemPadPx + 2);
-  g.smem = 2 * kChunkRows * pitch * sizeof(float2) + (WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3 + 4) * sizeof(int) +
-           kMetWarpsMax * 8 * sizeof(float);
+  g.smem = 2 * kChunkRows * pitch * sizeof(float2) + static_cast<size_t>(kChunkRows) * 4 * g.nwc * kWinBytes +
+           (WFK_NUM_POOLS * WFK_MAX_THRESHOLDS * 3 + 4) * sizeof(int) + 2 * 4 * kMaxColWarps * sizeof(float) +
+           kMaxColWarps * 8 * sizeof(float) + (64 * kMaxColWarps + 32) * sizeof(float);
   return g;
 }
 }  // namespace wfk
@@ -587,16 +638,29 @@ extern "C" int wfk_metrics(const float* pred, const float* tgt, int frames, int 
   p.nseg = g.nseg;
   const uintptr_t align = reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(tgt);
   p.vec2 = (w % 2 == 0 && (align & 7) == 0) ? 1 : 0;
-  p.vec4 = (w % 4 == 0 && (align & 15) == 0) ? 1 : 0;
+  // the kernel wants ascending thresholds (early exit of the compare loop); results are un-permuted by finalize
+  for (int i = 0; i < WFK_MAX_THRESHOLDS; ++i) p.perm[i] = i;
+  for (int i = 1; i < n_thresholds; ++i)
+    for (int j = i; j > 0 && p.thr[j] < p.thr[j - 1]; --j) {
+      const float tf_ = p.thr[j];
+      p.thr[j] = p.thr[j - 1];
+      p.thr[j - 1] = tf_;
+      const int ti_ = p.perm[j];
+      p.perm[j] = p.perm[j - 1];
+      p.perm[j - 1] = ti_;
+    }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static wfk::PerDeviceOnce attr_once;
   if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
-    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::metrics_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(wfk::metrics_geom(1, 64 * wfk::kMaxColWarps).smem)));
+    const int max_smem = static_cast<int>(wfk::metrics_geom(1, 64 * wfk::kMaxColWarps).smem);
+    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::metrics_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::metrics_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_lock.finished();
   }
-  wfk::metrics_strip_kernel<<<dim3(g.ns, g.nseg, frames), 32 * (g.nwc + 1), g.smem, s>>>(
-      p, static_cast<wfk::TileRec*>(workspace));
+  if (p.vec2)
+    wfk::metrics_strip_kernel<true><<<dim3(g.ns, g.nseg, frames), 32 * g.nwc, g.smem, s>>>(p, static_cast<wfk::TileRec*>(workspace));
+  else
+    wfk::metrics_strip_kernel<false><<<dim3(g.ns, g.nseg, frames), 32 * g.nwc, g.smem, s>>>(p, static_cast<wfk::TileRec*>(workspace));
   int rc = wfk::launched("metrics_strip_kernel");
   if (rc != WFK_OK) return rc;
   const size_t tile_bytes = (static_cast<size_t>(g.tiles()) * frames * sizeof(wfk::TileRec) + 255) & ~static_cast<size_t>(255);
@@ -604,6 +668,8 @@ extern "C" int wfk_metrics(const float* pred, const float* tgt, int frames, int 
   wfk::metrics_frame_kernel<<<frames, 128, 0, s>>>(static_cast<const wfk::TileRec*>(workspace), g.tiles(), h, w, frs);
   rc = wfk::launched("metrics_frame_kernel");
   if (rc != WFK_OK) return rc;
-  wfk::metrics_finalize_kernel<<<1, 128, 0, s>>>(frs, frames, n_thresholds, out);
+  wfk::ThrPerm perm;
+  for (int i = 0; i < WFK_MAX_THRESHOLDS; ++i) perm.v[i] = p.perm[i];
+  wfk::metrics_finalize_kernel<<<1, 1024, 0, s>>>(frs, frames, n_thresholds, perm, out);
   return wfk::launched("metrics_finalize_kernel");
 }

@@ -95,20 +95,39 @@ __global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
     int t_out, int hw, float* __restrict__ pred, float* __restrict__ tgt, double* __restrict__ loss_sums) {
   constexpr int C = 4;
   __shared__ uint4 s_b[KS * NT * 32];   // per (k-step, n-tile, lane): (b0_hi, b1_hi, b0_lo, b1_lo)
+  __shared__ float s_w[KS * 8 * NT * 8];  // raw weights, staged with coalesced loads first
   __shared__ float s_bias[NT * 8];
   __shared__ float s_red[kPredTcThreads / 32];
   const int K = t_in * C, N = t_out * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
+  // weights: one coalesced pass global -> shared (all loads in flight at once), then the split / fragment layout
+  // from shared memory. (Building the fragments straight from global memory cost 42 dependent L2 round trips per
+  // thread: 17 us of a 50 us kernel.)
+  {
+    constexpr int kPer = (KS * 8 * NT * 8 + kPredTcThreads - 1) / kPredTcThreads;
+    float wv[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = threadIdx.x + j * kPredTcThreads;
+      wv[j] = (i < N * K) ? __ldg(weight + i) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = threadIdx.x + j * kPredTcThreads;
+      if (i < KS * 8 * NT * 8) s_w[i] = wv[j];
+    }
+  }
+  for (int i = threadIdx.x; i < NT * 8; i += blockDim.x) s_bias[i] = i < N ? __ldg(bias + i) : 0.f;
+  __syncthreads();
   for (int i = threadIdx.x; i < KS * NT * 32; i += blockDim.x) {
     const int ln = i & 31, nt = (i >> 5) % NT, ks = (i >> 5) / NT;
     const int n = nt * 8 + (ln >> 2), k0 = ks * 8 + (ln & 3), k1 = k0 + 4;
-    const float w0 = (n < N && k0 < K) ? __ldg(weight + n * K + k0) : 0.f;
-    const float w1 = (n < N && k1 < K) ? __ldg(weight + n * K + k1) : 0.f;
+    const float w0 = (n < N && k0 < K) ? s_w[n * K + k0] : 0.f;
+    const float w1 = (n < N && k1 < K) ? s_w[n * K + k1] : 0.f;
     const uint32_t h0 = to_tf32(w0), h1 = to_tf32(w1);
     s_b[i] = make_uint4(h0, h1, to_tf32(w0 - __uint_as_float(h0)), to_tf32(w1 - __uint_as_float(h1)));
   }
-  for (int i = threadIdx.x; i < NT * 8; i += blockDim.x) s_bias[i] = i < N ? __ldg(bias + i) : 0.f;
   __syncthreads();
 
   const int64_t total = static_cast<int64_t>(b) * hw;
@@ -132,6 +151,20 @@ __global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
         xa[ks][hlf] = (valid && k < K) ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>(k) * hw)) : zero4;
       }
     }
+    // every other global read of the tile is issued here as well (target frames, the last input frame of the output
+    // channels): loaded where they are used, the 12 target loads of the epilogue each cost a full memory round trip
+    // (long-scoreboard stalls were 7 of every 8 warp cycles)
+    float4 last_o[2], tvv[NT][2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      last_o[e] = valid ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>((t_in - 1) * C + ((2 * t + e) & 3)) * hw)) : zero4;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int o = nt * 8 + 2 * t + e;
+        tvv[nt][e] = (valid && o < N) ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>(K + o) * hw)) : zero4;
+      }
     float acc[2][NT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -172,10 +205,6 @@ __global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
     }
     if (valid) {
       // outputs o = 8*nt + 2t + e: channel (2t + e) % 4; C fragment (c0, c2 | c0', c2') = pixels 0..3 for e = 0, (c1, c3 | ..) for e = 1
-      float4 last_o[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-        last_o[e] = __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>((t_in - 1) * C + ((2 * t + e) & 3)) * hw));
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
@@ -183,7 +212,7 @@ __global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
           const int o = nt * 8 + 2 * t + e;
           if (o < N) {
             const float bo = s_bias[o];
-            const float4 tv = __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>(K + o) * hw));
+            const float4 tv = tvv[nt][e];
             const float y0 = acc[0][nt][e] + bo, y1 = acc[0][nt][2 + e] + bo, y2 = acc[1][nt][e] + bo, y3 = acc[1][nt][2 + e] + bo;
             const float4 l = last_o[e];
             const float r0 = tv.x - l.x, r1 = tv.y - l.y, r2 = tv.z - l.z, r3 = tv.w - l.w;
@@ -225,7 +254,7 @@ extern "C" int wfk_predict_linear(const float* lat, const float* weight, const f
   if (c == 4 && K <= 56 && N == 48 && hw % 4 == 0 && (align & 15) == 0) {
     // Path-B shape (13 -> 12 frames, 4 channels): tensor-core kernel, persistent over 128-pixel tiles
     const int64_t tiles = (static_cast<int64_t>(b) * hw + wfk::kPredTcThreads - 1) / wfk::kPredTcThreads;
-    const int64_t cap = static_cast<int64_t>(wfk::num_sms()) * 4;
+    const int64_t cap = static_cast<int64_t>(wfk::num_sms()) * 2;   // 2 CTAs per SM are resident (240 registers)
     const unsigned blocks = static_cast<unsigned>(tiles < cap ? tiles : cap);
     wfk::predict_linear_tc_kernel<7, 6><<<blocks, wfk::kPredTcThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         lat, weight, bias, b, t_in, t_out, hw, pred, tgt, loss_sums);
