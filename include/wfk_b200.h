@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WFK_ABI_VERSION 1
+#define WFK_ABI_VERSION 2
 
 enum wfk_status {
   WFK_OK = 0,
@@ -44,6 +44,12 @@ int wfk_abi_version(void);
 int wfk_init(int device);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t wfk_launch_count(void);
+/* Non-finite guard. The kernels that read GroupNorm statistics (wfk_gn_table, wfk_groupnorm_apply) or write model
+ * outputs (the encoder's moments, the decoded frames) set a per-device host-mapped flag when they meet inf / NaN --
+ * which is what an fp16 activation beyond 65504 becomes one layer later. Returns WFK_OK or WFK_ERR_NONFINITE (detail in
+ * wfk_last_error); makes no CUDA call, so it is definitive only for work the caller has synchronised. reset != 0
+ * clears the flag. The reference (fp32 / TF32) has no such failure mode: resnet.py / vae.py run in the fp32 range. */
+int wfk_nonfinite_status(int device, int reset);
 
 /* ---------------------------------------------------------------------------------------------
  * a1  VIL frame staging.  Replaces SEVIRDataLoader.preprocess_data_dict + change_layout
@@ -143,7 +149,9 @@ int wfk_metrics(const float* pred, const float* tgt, int frames, int h, int w, c
                 size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * a3-a6, a9  Autoencoder building blocks (activations NHWC fp16 on device).
+ * a3-a6, a9  Autoencoder building blocks (activations NHWC, 16 bits per value on device: fp16 by default; the
+ *     entry points with a `bf16` argument / wfk_conv_desc.operand_bf16 read and write bf16 instead -- the whole chain
+ *     of one model must use one format).
  *
  * Implicit-GEMM convolution / GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
  * Replaces nn.Conv2d 3x3 / 1x1 (resnet.py:405,421,452; vae.py:24,68,103,148), Downsample2D
@@ -210,7 +218,7 @@ typedef struct wfk_conv_desc {
   int32_t out_sy, out_sx;/* output pixel = (y*out_sy + (phase>>1), x*out_sx + (phase&1))         */
   int32_t ldc;           /* output / residual channel pitch in elements                         */
   int32_t cpg;           /* channels per GroupNorm group (4, 8 or 16) when stats != NULL        */
-  int32_t operand_bf16;  /* 0: fp16 operands (default), 1: bf16 operands                        */
+  int32_t operand_bf16;  /* 0: fp16 operands and fp16 activation I/O (default), 1: bf16 for both      */
   const void* gn_table;  /* optional fused GroupNorm+SiLU on A source 0 (3x3 stride-1 convs only):
                             [n_frames][cin] float2 (scale, shift) from wfk_gn_table, or NULL          */
   /* Alternative to gn_table: derive (scale, shift) inside the kernel from the producer's raw statistics
@@ -243,7 +251,7 @@ void wfk_conv_plan_destroy(wfk_conv_plan* plan);
  * (resnet.py:457-458, 479-485; vae.py:82-83, 162-163; attention.py:141).  x, out: [n, hw, c] fp16;
  * stats: [n][groups][2] double (sum, sum of squares over the group's c/groups * hw values). */
 int wfk_groupnorm_apply(const void* x, const double* stats, const float* gamma, const float* beta, int n,
-                        int hw, int c, int groups, float eps, int apply_silu, void* out, void* stream);
+                        int hw, int c, int groups, float eps, int apply_silu, void* out, int bf16, void* stream);
 
 /* Per-(frame, channel) scale/shift of a GroupNorm whose apply (+SiLU) is fused into the consuming
  * convolution's operand staging: table[n][c] = (rstd*gamma, beta - mean*rstd*gamma). */
@@ -263,7 +271,7 @@ int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int w, const f
  * extra constant-one input plane (1 inside the image, 0 in the padding) carries the bias of a 1x1 convolution folded
  * in front (post_quant_conv, autoencoder_kl.py:87). cout a multiple of 128; cpg 4, 8 or 16 when stats != NULL. */
 int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w, int ones_plane, const void* weight_h,
-                        const float* bias, int cout, void* out, double* stats, int cpg, void* stream);
+                        const float* bias, int cout, void* out, double* stats, int cpg, int bf16, void* stream);
 
 /* Direct 3x3 (pad 1, stride 1) convolution for tiny output-channel counts, optional post 1x1.
  * Replaces decoder.conv_out (vae.py:148) and encoder.conv_out + quant_conv (vae.py:68,
@@ -332,12 +340,12 @@ int wfk_bcast_add_rows(const float* vec, const float* pos, int n, int tokens, in
  * stream; stats as wfk_groupnorm_apply; weight: [9][c] fp32 (tap-major); out: [n, 1, h, w] fp32. */
 int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const float* gamma, const float* beta, int n,
                            int h, int w, int c, int groups, float eps, const float* weight, float bias,
-                           float* out, void* stream);
+                           float* out, int bf16, void* stream);
 
 /* Row softmax: probs[r, :] = softmax(scale * scores[r, :]) in fp32, stored fp16.
  * Replaces torch.softmax(attention_scores.float(), dim=-1) (attention.py:171); `scale` is the
  * baddbmm alpha (attention.py:148, 168). */
-int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, void* stream);
+int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, int bf16, void* stream);
 
 /* f.4  ConvAttnModel latent compressor (experiments/v1_experiments/pretrained_ae_convattn_ae_sevir/train.py:58-170),
  *      whole network in one launch, one CTA per latent frame: x [n, cin, 48, 48] fp32 -> z [n, latent_dim] and

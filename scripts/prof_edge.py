@@ -24,17 +24,17 @@ img = torch.empty(n, 1, hw, hw, device=dev)
 for rep in range(3):
     stats.zero_()
     _cabi.check(lib.wfk_conv3x3_stem_tc(x.data_ptr(), n, 1, hw, hw, 0, w.data_ptr(), b.data_ptr(), c, out.data_ptr(),
-                                        stats.data_ptr(), 4, st), "stem")
+                                        stats.data_ptr(), 4, 0, st), "stem")
     _cabi.check(lib.wfk_gn_silu_conv3x3_c1(out.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), n, hw, hw,
-                                           c, 32, 1e-6, tail_w.data_ptr(), 0.1, img.data_ptr(), st), "tail")
+                                           c, 32, 1e-6, tail_w.data_ptr(), 0.1, img.data_ptr(), 0, st), "tail")
 torch.cuda.synchronize()
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 e0.record()
 _cabi.check(lib.wfk_conv3x3_stem_tc(x.data_ptr(), n, 1, hw, hw, 0, w.data_ptr(), b.data_ptr(), c, out.data_ptr(),
-                                    stats.data_ptr(), 4, st), "stem")
+                                    stats.data_ptr(), 4, 0, st), "stem")
 e1.record()
 _cabi.check(lib.wfk_gn_silu_conv3x3_c1(out.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), n, hw, hw, c,
-                                       32, 1e-6, tail_w.data_ptr(), 0.1, img.data_ptr(), st), "tail")
+                                       32, 1e-6, tail_w.data_ptr(), 0.1, img.data_ptr(), 0, st), "tail")
 e2.record()
 torch.cuda.synchronize()
 print(f"n={n}: stem {e0.elapsed_time(e1) * 1e3 / n:.1f} us/frame, tail {e1.elapsed_time(e2) * 1e3 / n:.1f} us/frame")

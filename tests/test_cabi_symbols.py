@@ -34,7 +34,7 @@ def test_binding_covers_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.wfk_abi_version() == 1
+    assert lib.wfk_abi_version() == 2
     assert lib.wfk_strerror(0) == b"ok"
     assert b"invalid" in lib.wfk_strerror(-1)
 
@@ -58,7 +58,7 @@ def test_no_silent_fallback_without_gpu(lib):
     with pytest.raises(RuntimeError):
         metrics.calc_metrics(torch.rand(1, 2, 1, 64, 64), torch.rand(1, 2, 1, 64, 64))
     # calls before wfk_init are refused by the library itself
-    assert lib.wfk_softmax_rows(None, 1, 8, 1.0, None, None) < 0
+    assert lib.wfk_softmax_rows(None, 1, 8, 1.0, None, 0, None) < 0
 
 
 def test_product_never_imports_oracle():

@@ -255,7 +255,7 @@ def test_softmax_rows(lib, rows, cols):
     s = torch.randn(rows, cols, device=DEV) * 7.0
     out = torch.empty(rows, cols, dtype=torch.float16, device=DEV)
     scale = 1.0 / math.sqrt(512)
-    _cabi.check(lib.wfk_softmax_rows(s.data_ptr(), rows, cols, scale, out.data_ptr(),
+    _cabi.check(lib.wfk_softmax_rows(s.data_ptr(), rows, cols, scale, out.data_ptr(), 0,
                                      torch.cuda.current_stream().cuda_stream), "softmax")
     want = torch.softmax(s.float().cpu() * scale, dim=-1)
     assert (out.float().cpu() - want).abs().max().item() < 1e-3   # fp16 output
@@ -297,7 +297,7 @@ def test_stem_tc_vs_conv2d(lib, n, cin, h, w, cout, ones, cpg):
     stats = torch.zeros(n, groups, 2, dtype=torch.float64, device=DEV)
     xd, wd, bd = x.to(DEV), wp16.to(DEV), bias.to(DEV)
     _cabi.check(lib.wfk_conv3x3_stem_tc(xd.data_ptr(), n, cin, h, w, ones, wd.data_ptr(), bd.data_ptr(), cout,
-                                        out.data_ptr(), stats.data_ptr(), cpg, torch.cuda.current_stream().cuda_stream), "stem")
+                                        out.data_ptr(), stats.data_ptr(), cpg, 0, torch.cuda.current_stream().cuda_stream), "stem")
     # reference on the SAME rounded operands: fp16 input planes (+ the ones plane), fp16 packed weights
     planes = x.half().float()
     if ones:

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <new>
 
+#include "act16.cuh"
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -209,7 +210,7 @@ __device__ __forceinline__ int warp_transpose_reduce32(float (&v)[32], int lane)
   return idx;
 }
 
-template <int BN, int MB, int STAGES, bool PAIR, bool HALO, bool EPI>
+template <int BN, int MB, int STAGES, bool PAIR, bool HALO, bool EPI, bool BF16>
 __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
     conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr int kXformWarps = xform_warps(HALO, MB);
@@ -689,18 +690,18 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
 #pragma unroll
               for (int j = 0; j < kXfGroup; ++j) {
                 if (!ok[j]) continue;
-                __half2* h2 = reinterpret_cast<__half2*>(&u[j]);
+                uint32_t* h2 = reinterpret_cast<uint32_t*>(&u[j]);
                 if (WFK_XDBG(p) != 1) {
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     // packed fp32x2 FMAs (sm_100): same rounding per component, half the issue slots
-                    const float2 v = __ffma2_rn(__half22float2(h2[e]), make_float2(ga[2 * e], ga[2 * e + 1]),
+                    const float2 v = __ffma2_rn(A16<BF16>::unpack(h2[e]), make_float2(ga[2 * e], ga[2 * e + 1]),
                                                 make_float2(gb[2 * e], gb[2 * e + 1]));
                     float2 t;
                     asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(v.x));
                     asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(v.y));
                     const float2 y = __ffma2_rn(v, t, v);
-                    h2[e] = __floats2half2_rn(y.x, y.y);
+                    h2[e] = A16<BF16>::pack(y.x, y.y);
                   }
                 }
                 sts_v4(addr[j], u[j]);
@@ -992,10 +993,10 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (j < nvec) {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&rrow[j]);
+                const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&rrow[j]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float2 f = __half22float2(h2[e]);
+                  const float2 f = A16<BF16>::unpack(h2[e]);
                   v[8 * j + 2 * e + 0] += f.x;
                   v[8 * j + 2 * e + 1] += f.y;
                 }
@@ -1038,9 +1039,9 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
             for (int j = 0; j < 4; ++j) {
               if (j < nvec) {
                 uint4 u;
-                __half2* h2 = reinterpret_cast<__half2*>(&u);
+                uint32_t* h2 = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                for (int e = 0; e < 4; ++e) h2[e] = A16<BF16>::pack(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
                 op[j] = u;
               }
             }
@@ -1049,9 +1050,9 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           uint4 up[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __half2* h2 = reinterpret_cast<__half2*>(&up[j]);
+            uint32_t* h2 = reinterpret_cast<uint32_t*>(&up[j]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            for (int e = 0; e < 4; ++e) h2[e] = A16<BF16>::pack(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
           }
 #pragma unroll
           for (int ps = 0; ps < kStPasses; ++ps) {
@@ -1107,13 +1108,13 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
               for (int j = 0; j < 4; ++j) {
                 if (j < nvec) {
                   uint4 u;
-                  __half2* h2 = reinterpret_cast<__half2*>(&u);
+                  uint32_t* h2 = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const int i0 = 8 * j + 2 * e;
                     const float a = act_apply(p.act2, fmaf(v[i0], s_sc2[c0 + i0], s_sh2[c0 + i0]), p.act_slope);
                     const float b = act_apply(p.act2, fmaf(v[i0 + 1], s_sc2[c0 + i0 + 1], s_sh2[c0 + i0 + 1]), p.act_slope);
-                    h2[e] = __floats2half2_rn(a, b);
+                    h2[e] = A16<BF16>::pack(a, b);
                   }
                   op[j] = u;
                 }
@@ -1208,10 +1209,10 @@ constexpr size_t conv_smem_bytes() {
          kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + kEpiWarps * (HALO ? (BN == 256 ? 1024 : 2048) : 4096) + 64;
 }
 
-template <int BN, bool PAIR, bool HALO, bool EPI = false>
+template <int BN, bool PAIR, bool HALO, bool EPI = false, bool BF16 = false>
 cudaError_t launch_conv(const ConvKernelParams& params, int grid, cudaStream_t s) {
   using Cfg = ConvCfg<BN, PAIR, HALO>;
-  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, PAIR, HALO, EPI>;
+  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, PAIR, HALO, EPI, BF16>;
   static wfk::PerDeviceOnce attr_once;
   if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1245,7 +1246,7 @@ int max_active_pairs() {
   static std::atomic<int> cached_dev[kMaxDevices];   // zero-initialised: 0 = not queried yet (per device)
   const int dev = t_device < 0 ? 0 : t_device;
   if (cached_dev[dev].load() > 0) return cached_dev[dev].load();
-  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, true, HALO, false>;
+  auto kern = conv_gemm_kernel<BN, Cfg::kMB, Cfg::kStages, true, HALO, false, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(conv_smem_bytes<BN, true, HALO>()));
   cudaLaunchConfig_t cfg{};
@@ -1274,6 +1275,7 @@ struct wfk_conv_plan {
   int pair;
   int halo;
   int epi;   // extended epilogue (activation / second activated output): EPI kernel variants
+  int bf16;  // bf16 operands / activations (CTA-pair kernels without the extended epilogue only)
   int grid;
   int device;
 };
@@ -1492,6 +1494,11 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.scale2 = d->scale2;
   p.shift2 = d->shift2;
   plan->epi = (d->act != 0 || d->out2_h != nullptr) ? 1 : 0;
+  plan->bf16 = d->operand_bf16 ? 1 : 0;
+  if (plan->bf16 && (plan->epi || !plan->pair)) {
+    delete plan;
+    return wfk::fail(WFK_ERR_INVALID, "bf16 operands are built for the CTA-pair kernels without activation epilogues only");
+  }
   if (plan->epi && !plan->pair) {
     delete plan;
     return wfk::fail(WFK_ERR_INVALID, "activation epilogues need the CTA-pair kernels (WFK_CONV_PAIR=0 is set)");
@@ -1560,6 +1567,13 @@ extern "C" int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream) {
     else
       e = (plan->bn == 256) ? wfk::launch_conv<256, true, false, true>(plan->params, plan->grid, s)
                             : wfk::launch_conv<128, true, false, true>(plan->params, plan->grid, s);
+  } else if (plan->bf16) {
+    if (plan->halo)
+      e = (plan->bn == 256) ? wfk::launch_conv<256, true, true, false, true>(plan->params, plan->grid, s)
+                            : wfk::launch_conv<128, true, true, false, true>(plan->params, plan->grid, s);
+    else
+      e = (plan->bn == 256) ? wfk::launch_conv<256, true, false, false, true>(plan->params, plan->grid, s)
+                            : wfk::launch_conv<128, true, false, false, true>(plan->params, plan->grid, s);
   } else if (plan->halo) {
     e = (plan->bn == 256) ? wfk::launch_conv<256, true, true>(plan->params, plan->grid, s)
                           : wfk::launch_conv<128, true, true>(plan->params, plan->grid, s);

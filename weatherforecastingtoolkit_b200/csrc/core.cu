@@ -7,6 +7,8 @@ std::atomic<int64_t> g_launches{0};
 std::atomic<uint64_t> g_init_mask{0};
 int g_num_sms_dev[kMaxDevices] = {0};
 thread_local int t_device = -1;
+int* g_flag_host[kMaxDevices] = {nullptr};
+int* g_flag_dev[kMaxDevices] = {nullptr};
 EncodeTiledFn g_encode_tiled = nullptr;
 static std::mutex g_init_mu;
 
@@ -78,6 +80,19 @@ extern "C" const char* wfk_last_error(void) { return wfk::g_last_error; }
 extern "C" int wfk_abi_version(void) { return WFK_ABI_VERSION; }
 extern "C" int64_t wfk_launch_count(void) { return wfk::g_launches.load(); }
 
+extern "C" int wfk_nonfinite_status(int device, int reset) {
+  if (device < 0 || device >= wfk::kMaxDevices || wfk::g_flag_host[device] == nullptr)
+    return wfk::fail(WFK_ERR_NOT_INIT, "wfk_init(%d) was not called", device);
+  volatile int* f = wfk::g_flag_host[device];
+  const int v = *f;
+  if (v != 0 && reset) *f = 0;
+  if (v != 0)
+    return wfk::fail(WFK_ERR_NONFINITE,
+                     "a GroupNorm statistic or model output went inf / NaN on device %d (stage mask 0x%x): with fp16 "
+                     "activations this is what a value beyond 65504 turns into; bf16 operands have the fp32 range", device, v);
+  return WFK_OK;
+}
+
 // Registers `device` with the library (any number of devices, from any thread). The caller's current device is left
 // as it was: every later entry point selects the device of its stream / pointers itself.
 extern "C" int wfk_init(int device) {
@@ -107,6 +122,19 @@ extern "C" int wfk_init(int device) {
       return wfk::fail(WFK_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     }
     if (ce == cudaSuccess) wfk::g_encode_tiled = reinterpret_cast<wfk::EncodeTiledFn>(fn);
+  }
+  if (ce == cudaSuccess && wfk::g_flag_host[device] == nullptr) {
+    int* hp = nullptr;
+    int* dp = nullptr;
+    ce = cudaHostAlloc(reinterpret_cast<void**>(&hp), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (ce == cudaSuccess) {
+      *hp = 0;
+      ce = cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), hp, 0);
+    }
+    if (ce == cudaSuccess) {
+      wfk::g_flag_host[device] = hp;
+      wfk::g_flag_dev[device] = dp;
+    }
   }
   if (prev != device) cudaSetDevice(prev);
   if (ce != cudaSuccess) return wfk::fail(WFK_ERR_CUDA, "initialising device %d failed: %s", device, cudaGetErrorString(ce));

@@ -1,17 +1,18 @@
 // HBM-bound passes between the tensor-core kernels: GroupNorm apply (+SiLU), row softmax,
 // fp32 -> fp16 weight conversion. All use 128-bit vector loads/stores on NHWC fp16 activations.
-#include <cuda_fp16.h>
-
+#include "act16.cuh"
 #include "internal.h"
 
 namespace wfk {
 
 // y = silu?( (x - mean) * rstd * gamma + beta ), with mean / rstd from the (sum, sumsq) pairs the
 // producing kernel accumulated. One block = `ppb` pixels of one frame, all channels.
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, const double* __restrict__ stats,
+template <bool BF16>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restrict__ x, const double* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int hw, int c, int groups,
-                                                       float eps, int apply_silu, __half* __restrict__ out, int ppb) {
+                                                       float eps, int apply_silu, uint16_t* __restrict__ out, int ppb,
+                                                       int* __restrict__ nonfinite) {
   extern __shared__ float s_ab[];  // a[c], b[c], then mean[groups], rstd[groups]
   float* s_a = s_ab;
   float* s_b = s_ab + c;
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     const int g = threadIdx.x;
     const double sum = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 0];
     const double sq = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 1];
+    if (!(isfinite(sum) && isfinite(sq))) *nonfinite = 2;
     const double mean = sum / cnt;
     double var = sq / cnt - mean * mean;
     var = var < 0.0 ? 0.0 : var;
@@ -65,17 +67,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     for (int k = 0; k < U; ++k) {
       const int v = v0 + k * blockDim.x;
       if (v < total) {
-        __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
+        uint32_t* h2 = reinterpret_cast<uint32_t*>(&u[k]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float2 f = __half22float2(h2[e]);
+          float2 f = A16<BF16>::unpack(h2[e]);
           f.x = fmaf(f.x, ra[2 * e], rb[2 * e]);
           f.y = fmaf(f.y, ra[2 * e + 1], rb[2 * e + 1]);
           if (apply_silu) {
             f.x = __fdividef(f.x, 1.f + __expf(-f.x));
             f.y = __fdividef(f.y, 1.f + __expf(-f.y));
           }
-          h2[e] = __floats2half2_rn(f.x, f.y);
+          h2[e] = A16<BF16>::pack(f.x, f.y);
         }
         yout[v] = u[k];
       }
@@ -84,8 +86,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
 }
 
 // probs[r, :] = softmax(scale * scores[r, :]); one block per row, row staged in shared memory.
+template <bool BF16>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ scores, int cols, float scale,
-                                                           __half* __restrict__ probs) {
+                                                           uint16_t* __restrict__ probs) {
   extern __shared__ float s_row[];
   __shared__ float s_red[8];
   const int64_t r = blockIdx.x;
@@ -114,14 +117,15 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   sum = 0.f;
   for (int i = 0; i < (blockDim.x >> 5); ++i) sum += s_red[i];
   const float inv = 1.f / sum;
-  __half* dst = probs + r * cols;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) dst[i] = __float2half_rn(s_row[i] * inv);
+  uint16_t* dst = probs + r * cols;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) dst[i] = A16<BF16>::pack1(s_row[i] * inv);
 }
 
 // Same for cols % 4 == 0 and cols <= 4096: the row lives in registers (up to 4 float4 per thread), one 128-bit
 // load and one 64-bit store per 4 elements, two block reductions. HBM-bound: 6 bytes per score.
+template <bool BF16>
 __global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __restrict__ scores, int cols, float scale,
-                                                               __half* __restrict__ probs) {
+                                                               uint16_t* __restrict__ probs) {
   __shared__ float s_red[2][8];
   const int64_t r = blockIdx.x;
   const float4* src = reinterpret_cast<const float4*>(scores + r * cols);
@@ -166,8 +170,8 @@ __global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __re
     const int i = threadIdx.x + k * 256;
     if (i < nvec) {
       uint2 u;
-      *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[k].x * inv, v[k].y * inv);
-      *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[k].z * inv, v[k].w * inv);
+      u.x = A16<BF16>::pack(v[k].x * inv, v[k].y * inv);
+      u.y = A16<BF16>::pack(v[k].z * inv, v[k].w * inv);
       dst[i] = u;
     }
   }
@@ -176,14 +180,17 @@ __global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __re
 // (scale, shift) per (frame, channel) of a GroupNorm, for consumers that fuse the apply step.
 __global__ void gn_table_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int hw, int c, int groups, float eps,
-                                float2* __restrict__ table) {
+                                float2* __restrict__ table, int* __restrict__ nonfinite) {
   const int n = blockIdx.x;
   const int cpg = c / groups;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     const int g = ch / cpg;
     const double cnt = static_cast<double>(cpg) * hw;
-    const double mean = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 0] / cnt;
-    double var = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 1] / cnt - mean * mean;
+    const double s0 = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 0];
+    const double s1 = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 1];
+    if (!(isfinite(s0) && isfinite(s1))) *nonfinite = 1;   // benign race: every writer stores the same value
+    const double mean = s0 / cnt;
+    double var = s1 / cnt - mean * mean;
     var = var < 0.0 ? 0.0 : var;
     const float rstd = static_cast<float>(rsqrt(var + static_cast<double>(eps)));
     const float a = rstd * gamma[ch];
@@ -193,13 +200,15 @@ __global__ void gn_table_kernel(const double* __restrict__ stats, const float* _
 
 // [n, hw, c] fp32 -> [n, c, hw] fp32 (the model-facing layout of the moments tensor)
 __global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int64_t total, int hw, int c,
-                                        float* __restrict__ out) {
+                                        float* __restrict__ out, int* __restrict__ nonfinite) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // index into out
   if (i >= total) return;
   const int p = static_cast<int>(i % hw);
   const int ch = static_cast<int>((i / hw) % c);
   const int64_t n = i / (static_cast<int64_t>(hw) * c);
-  out[i] = in[(n * hw + p) * c + ch];
+  const float v = in[(n * hw + p) * c + ch];
+  if (!isfinite(v)) *nonfinite = 4;   // the encoder's moments: the last tensor of encode
+  out[i] = v;
 }
 
 // DiagonalGaussianDistribution arithmetic in one pass over the moments tensor [n, 2*lc, hw]:
@@ -232,7 +241,8 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, int64_t n, __hal
 }  // namespace wfk
 
 extern "C" int wfk_groupnorm_apply(const void* x, const double* stats, const float* gamma, const float* beta, int n,
-                                   int hw, int c, int groups, float eps, int apply_silu, void* out, void* stream) {
+                                   int hw, int c, int groups, float eps, int apply_silu, void* out, int bf16,
+                                   void* stream) {
   WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(x && stats && gamma && beta && out, "null pointer");
   WFK_REQUIRE(n > 0 && hw > 0 && c > 0 && groups > 0, "empty problem");
@@ -242,8 +252,13 @@ extern "C" int wfk_groupnorm_apply(const void* x, const double* stats, const flo
   int ppb = 65536 / c;  // 128 KB of fp16 per block: amortises the per-block scale/shift prologue
   if (ppb < 1) ppb = 1;
   dim3 grid((hw + ppb - 1) / ppb, n);
-  wfk::gn_apply_kernel<<<grid, 256, (2 * c + 2 * groups) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), stats, gamma, beta, hw, c, groups, eps, apply_silu, static_cast<__half*>(out), ppb);
+  const size_t smem = (2 * c + 2 * groups) * sizeof(float);
+  if (bf16)
+    wfk::gn_apply_kernel<true><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t*>(x), stats, gamma, beta, hw, c, groups, eps, apply_silu, static_cast<uint16_t*>(out), ppb, wfk::nonfinite_flag());
+  else
+    wfk::gn_apply_kernel<false><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t*>(x), stats, gamma, beta, hw, c, groups, eps, apply_silu, static_cast<uint16_t*>(out), ppb, wfk::nonfinite_flag());
   return wfk::launched("gn_apply_kernel");
 }
 
@@ -253,21 +268,30 @@ extern "C" int wfk_gn_table(const double* stats, const float* gamma, const float
   WFK_REQUIRE(stats && gamma && beta && table, "null pointer");
   WFK_REQUIRE(n > 0 && hw > 0 && c > 0 && groups > 0 && c % groups == 0, "bad shape");
   wfk::gn_table_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats, gamma, beta, hw, c, groups, eps,
-                                                                        static_cast<float2*>(table));
+                                                                        static_cast<float2*>(table), wfk::nonfinite_flag());
   return wfk::launched("gn_table_kernel");
 }
 
-extern "C" int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, void* stream) {
+extern "C" int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, int bf16,
+                                void* stream) {
   WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(scores && probs, "null pointer");
   WFK_REQUIRE(rows > 0 && rows < (1ll << 31) && cols > 0 && cols <= 11264, "unsupported softmax shape");
   if (cols % 4 == 0 && cols <= 4096) {
-    wfk::softmax_rows_vec_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        scores, cols, scale, static_cast<__half*>(probs));
+    if (bf16)
+      wfk::softmax_rows_vec_kernel<true><<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          scores, cols, scale, static_cast<uint16_t*>(probs));
+    else
+      wfk::softmax_rows_vec_kernel<false><<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          scores, cols, scale, static_cast<uint16_t*>(probs));
     return wfk::launched("softmax_rows_vec_kernel");
   }
-  wfk::softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, cols * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      scores, cols, scale, static_cast<__half*>(probs));
+  if (bf16)
+    wfk::softmax_rows_kernel<true><<<static_cast<unsigned>(rows), 256, cols * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        scores, cols, scale, static_cast<uint16_t*>(probs));
+  else
+    wfk::softmax_rows_kernel<false><<<static_cast<unsigned>(rows), 256, cols * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        scores, cols, scale, static_cast<uint16_t*>(probs));
   return wfk::launched("softmax_rows_kernel");
 }
 
@@ -287,7 +311,7 @@ extern "C" int wfk_nhwc_to_nchw_f32(const float* in, int n, int hw, int c, float
   WFK_REQUIRE(in && out && n > 0 && hw > 0 && c > 0, "bad argument");
   const int64_t total = static_cast<int64_t>(n) * hw * c;
   wfk::nhwc_to_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, total, hw, c, out);
+      in, total, hw, c, out, wfk::nonfinite_flag());
   return wfk::launched("nhwc_to_nchw_f32_kernel");
 }
 

@@ -21,6 +21,12 @@ extern std::atomic<uint64_t> g_init_mask;     // bit d set once wfk_init(d) succ
 extern int g_num_sms_dev[kMaxDevices];
 extern thread_local int t_device;             // device of the innermost DeviceScope of this thread (-1 outside)
 inline int num_sms() { return t_device >= 0 ? g_num_sms_dev[t_device] : 0; }
+// Non-finite guard: one host-mapped int per device, set (never cleared) by the kernels that see GroupNorm statistics or
+// model outputs go inf / NaN -- what an fp16 activation beyond 65504 turns into one layer later. Read through
+// wfk_nonfinite_status() without any CUDA call; definitive after the stream has been synchronised.
+extern int* g_flag_host[kMaxDevices];
+extern int* g_flag_dev[kMaxDevices];
+inline int* nonfinite_flag() { return t_device >= 0 ? g_flag_dev[t_device] : nullptr; }
 
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;

@@ -11,6 +11,7 @@
 
 #include <cstdlib>
 
+#include "act16.cuh"
 #include "internal.h"
 
 namespace wfk {
@@ -36,19 +37,18 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
+template <bool BF16>
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                           uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  const uint32_t a[4] = {a0, a1, a2, a3};
+  mma_16816<BF16>(c, a, b0, b1);
 }
 
-template <int KSTEPS>
+template <int KSTEPS, bool BF16>
 __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3x3_c1_tc_kernel(
-    const __half* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+    const uint16_t* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, int h, int w, int groups, float eps, const float* __restrict__ wt, float bias,
-    float* __restrict__ out) {
+    float* __restrict__ out, int* __restrict__ nonfinite) {
   constexpr int C = KSTEPS * 16;
   constexpr int kPitch = C + 8;  // halfs per staged pixel row (16-byte pad: conflict-free ldmatrix)
   extern __shared__ __align__(16) uint8_t s_raw[];
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
   float* s_b = s_a + C;                                // [C]
   float* s_d = s_b + C;                                // [kTcMTiles*16][9]
   uint2* s_bf = reinterpret_cast<uint2*>(s_d + kTcMTiles * 16 * 9);       // [KSTEPS][2][32] weight fragments
-  __half* s_t = reinterpret_cast<__half*>(s_bf + KSTEPS * 2 * 32);    // [kTcWarps][16][kPitch]
+  uint16_t* s_t = reinterpret_cast<uint16_t*>(s_bf + KSTEPS * 2 * 32);    // [kTcWarps][16][kPitch]
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ int s_pixoff[kTcMTiles * 16];   // halo pixel q -> element offset of its channel 0 relative to the tile origin
   const int n = blockIdx.z;
@@ -93,10 +93,8 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
     const int k = ks * 16 + (ln & 3) * 2;
     uint2 b = make_uint2(0u, 0u);
     if (tap < 9) {
-      const __half2 p0 = __floats2half2_rn(__ldg(wt + tap * C + k), __ldg(wt + tap * C + k + 1));
-      const __half2 p1 = __floats2half2_rn(__ldg(wt + tap * C + k + 8), __ldg(wt + tap * C + k + 9));
-      b.x = *reinterpret_cast<const uint32_t*>(&p0);
-      b.y = *reinterpret_cast<const uint32_t*>(&p1);
+      b.x = A16<BF16>::pack(__ldg(wt + tap * C + k), __ldg(wt + tap * C + k + 1));
+      b.y = A16<BF16>::pack(__ldg(wt + tap * C + k + 8), __ldg(wt + tap * C + k + 9));
     }
     s_bf[i] = b;
   }
@@ -104,7 +102,7 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
   constexpr int kChunks = C / 8;                 // 16-byte chunks per pixel
   constexpr int kIters = 16 * kChunks / 32;      // loads per lane per m-tile
   static_assert((16 * kChunks) % 32 == 0, "C must be a multiple of 16");
-  __half* my_t = s_t + warp * 16 * kPitch;
+  uint16_t* my_t = s_t + warp * 16 * kPitch;
   const uint32_t my_t_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(my_t));
   // every load of a lane hits the SAME 8-channel chunk (32 % kChunks == 0): its scale / shift pairs live in registers.
   // (Re-reading them from shared memory per load was 4x the tile's own bytes and saturated the L1 / shared pipe.)
@@ -130,7 +128,7 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
     if (y0 >= 1 && y0 + kOT < h && x0 >= 1 && x0 + kOT < w) {
       // interior tile: every halo pixel is inside the image; the address is the tile origin plus a per-pixel table
       // entry (the general path below spends ~20 integer instructions per 16-byte load on coordinates and clamps)
-      const __half* origin = x + ((static_cast<int64_t>(n) * h + y0) * w + x0) * C + (lane % kChunks) * 8;
+      const uint16_t* origin = x + ((static_cast<int64_t>(n) * h + y0) * w + x0) * C + (lane % kChunks) * 8;
       okmask = (1u << kIters) - 1u;
 #pragma unroll
       for (int it = 0; it < kIters; ++it)
@@ -160,16 +158,16 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (okmask & (1u << it)) {
         v = u[it];
-        __half2* h2 = reinterpret_cast<__half2*>(&v);
+        uint32_t* h2 = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 hv = __ffma2_rn(__half22float2(h2[e]), make_float2(ga[2 * e], ga[2 * e + 1]),
+          const float2 hv = __ffma2_rn(A16<BF16>::unpack(h2[e]), make_float2(ga[2 * e], ga[2 * e + 1]),
                                        make_float2(gb[2 * e], gb[2 * e + 1]));
           float2 tv;
           asm("tanh.approx.f32 %0, %1;" : "=f"(tv.x) : "f"(hv.x));
           asm("tanh.approx.f32 %0, %1;" : "=f"(tv.y) : "f"(hv.y));
           const float2 yv = __ffma2_rn(hv, tv, hv);
-          h2[e] = __floats2half2_rn(yv.x, yv.y);
+          h2[e] = A16<BF16>::pack(yv.x, yv.y);
         }
       }
       *reinterpret_cast<uint4*>(my_t + pl * kPitch + ck * 8) = v;
@@ -182,8 +180,8 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
       const uint32_t addr = my_t_u32 + static_cast<uint32_t>(((lane & 15) * kPitch + ks * 16 + (lane >> 4) * 8) * 2);
       ldmatrix_x4(addr, a0, a1, a2, a3);
       const uint2 bf0 = s_bf[(ks * 2 + 0) * 32 + lane], bf1 = s_bf[(ks * 2 + 1) * 32 + lane];
-      mma_16816(acc[0], a0, a1, a2, a3, bf0.x, bf0.y);
-      mma_16816(acc[1], a0, a1, a2, a3, bf1.x, bf1.y);
+      mma_16816<BF16>(acc[0], a0, a1, a2, a3, bf0.x, bf0.y);
+      mma_16816<BF16>(acc[1], a0, a1, a2, a3, bf1.x, bf1.y);
     }
     // C fragment: rows lane/4 and lane/4 + 8, taps nt*8 + (lane%4)*2 + {0, 1}
 #pragma unroll
@@ -209,6 +207,7 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int s = 0; s < 3; ++s) acc += sd[((py + r) * kOH + (pxx + s)) * 9 + r * 3 + s];
+        if (!isfinite(acc)) *nonfinite = 8;   // decoded frame: the last tensor of decode
         out[(static_cast<int64_t>(n) * h + y) * w + xx] = acc;
       }
     }
@@ -226,23 +225,23 @@ __global__ void __launch_bounds__(kTcThreads, KSTEPS <= 8 ? 4 : 2) gn_silu_conv3
   }
 }
 
-template <int KSTEPS>
-int launch_tail_tc(const __half* x, const double* stats, const float* gamma, const float* beta, int n, int h, int w,
+template <int KSTEPS, bool BF16>
+int launch_tail_tc(const uint16_t* x, const double* stats, const float* gamma, const float* beta, int n, int h, int w,
                    int groups, float eps, const float* weight, float bias, float* out, cudaStream_t s) {
   constexpr int C = KSTEPS * 16;
   const size_t smem = (2 * C + kTcMTiles * 16 * 9) * sizeof(float) + static_cast<size_t>(KSTEPS) * 2 * 32 * 8 +
                       static_cast<size_t>(kTcWarps) * 16 * (C + 8) * 2;
   static wfk::PerDeviceOnce attr_once;
   if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(gn_silu_conv3x3_c1_tc_kernel<KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gn_silu_conv3x3_c1_tc_kernel<KSTEPS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return fail(WFK_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_lock.finished();
   }
   const int tiles_x = (w + kOT - 1) / kOT;
   dim3 grid((tiles_x + kTcStrip - 1) / kTcStrip, (h + kOT - 1) / kOT, n);
-  gn_silu_conv3x3_c1_tc_kernel<KSTEPS><<<grid, kTcThreads, smem, s>>>(x, stats, gamma, beta, h, w, groups, eps, weight,
-                                                                    bias, out);
+  gn_silu_conv3x3_c1_tc_kernel<KSTEPS, BF16><<<grid, kTcThreads, smem, s>>>(x, stats, gamma, beta, h, w, groups, eps, weight,
+                                                                          bias, out, nonfinite_flag());
   return launched("gn_silu_conv3x3_c1_tc_kernel");
 }
 
@@ -250,7 +249,7 @@ int launch_tail_tc(const __half* x, const double* stats, const float* gamma, con
 __global__ void __launch_bounds__(kOutThreads) gn_silu_conv3x3_c1_kernel(
     const __half* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, int h, int w, int c, int groups, float eps, const float* __restrict__ wt,
-    float bias, float* __restrict__ out) {
+    float bias, float* __restrict__ out, int* __restrict__ nonfinite) {
   extern __shared__ float s_mem[];
   float* s_a = s_mem;                // [c]
   float* s_b = s_a + c;              // [c]
@@ -337,18 +336,25 @@ __global__ void __launch_bounds__(kOutThreads) gn_silu_conv3x3_c1_kernel(
 
 extern "C" int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const float* gamma, const float* beta, int n,
                                       int h, int w, int c, int groups, float eps, const float* weight, float bias,
-                                      float* out, void* stream) {
+                                      float* out, int bf16, void* stream) {
   WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(x && stats && gamma && beta && weight && out, "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0, "bad shape");
   WFK_REQUIRE(c % 8 == 0 && c > 0 && c <= 1024 && c % groups == 0 && groups <= 256, "unsupported c=%d groups=%d", c, groups);
   if (groups <= 64 && !std::getenv("WFK_TAIL_CUDA_CORES")) {
-    const __half* xh = static_cast<const __half*>(x);
+    const uint16_t* xh = static_cast<const uint16_t*>(x);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (c == 128) return wfk::launch_tail_tc<8>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
-    if (c == 64) return wfk::launch_tail_tc<4>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
-    if (c == 256) return wfk::launch_tail_tc<16>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
+    if (bf16) {
+      if (c == 128) return wfk::launch_tail_tc<8, true>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
+      if (c == 64) return wfk::launch_tail_tc<4, true>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
+      if (c == 256) return wfk::launch_tail_tc<16, true>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
+    } else {
+      if (c == 128) return wfk::launch_tail_tc<8, false>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
+      if (c == 64) return wfk::launch_tail_tc<4, false>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
+      if (c == 256) return wfk::launch_tail_tc<16, false>(xh, stats, gamma, beta, n, h, w, groups, eps, weight, bias, out, st);
+    }
   }
+  WFK_REQUIRE(!bf16, "bf16 activations: the CUDA-core tail kernel is fp16 only (c must be 64, 128 or 256)");
   const size_t smem = (static_cast<size_t>(c) * 11 + wfk::kOH * wfk::kOH * 9 + 2 * groups) * sizeof(float);
   static wfk::PerDeviceOnce attr_once;
   if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
@@ -358,6 +364,6 @@ extern "C" int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const 
   WFK_REQUIRE(smem <= 100 * 1024, "channel count too large for shared memory");
   dim3 grid((w + wfk::kOT - 1) / wfk::kOT, (h + wfk::kOT - 1) / wfk::kOT, n);
   wfk::gn_silu_conv3x3_c1_kernel<<<grid, wfk::kOutThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), stats, gamma, beta, h, w, c, groups, eps, weight, bias, out);
+      static_cast<const __half*>(x), stats, gamma, beta, h, w, c, groups, eps, weight, bias, out, wfk::nonfinite_flag());
   return wfk::launched("gn_silu_conv3x3_c1_kernel");
 }

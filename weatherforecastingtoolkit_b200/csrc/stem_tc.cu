@@ -7,8 +7,7 @@
 // [K x 128] weight fragments live in shared memory, and one warp produces 16 pixels x 128 channels per step.
 // The CUDA-core kernels they replace (edge_convs.cu / in_conv.cu) needed 9*cin FMAs per output value and ran 5-13x
 // above the HBM time of the layer. Also accumulates the GroupNorm (sum, sum of squares) of the fp32 result.
-#include <cuda_fp16.h>
-
+#include "act16.cuh"
 #include "internal.h"
 
 namespace wfk {
@@ -18,22 +17,15 @@ constexpr int kStemTcThreads = kStemTcWarps * 32;
 constexpr int kStemTcN = 128;           // channels per block (16 n8-tiles)
 constexpr int kStemTcPitch = kStemTcN + 8;
 
-__device__ __forceinline__ void stem_mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 // in [n, cin, h, w] fp32; wt [KSTEPS*16][cout] fp16 with row k = ci*9 + tap (ci = cin is the constant-one plane when
 // `ones_plane`), zero rows beyond K; out [n, h, w, cout] fp16; stats [n][cout/cpg][2] double.
-template <int KSTEPS>
+template <int KSTEPS, bool BF16>
 __global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_stem_tc_kernel(
-    const float* __restrict__ in, int cin, int ones_plane, int h, int w, const __half* __restrict__ wt,
-    const float* __restrict__ bias, int cout, __half* __restrict__ out, double* __restrict__ stats, int cpg,
+    const float* __restrict__ in, int cin, int ones_plane, int h, int w, const uint16_t* __restrict__ wt,
+    const float* __restrict__ bias, int cout, uint16_t* __restrict__ out, double* __restrict__ stats, int cpg,
     int tiles_per_warp) {
   __shared__ uint2 s_bf[KSTEPS][16][32];
-  __shared__ __align__(16) __half s_tile[kStemTcWarps][16][kStemTcPitch];
+  __shared__ __align__(16) uint16_t s_tile[kStemTcWarps][16][kStemTcPitch];
   __shared__ float s_bias[kStemTcN];
   __shared__ float s_stats[kStemTcWarps][kStemTcN / 4][2];
   const int n = blockIdx.y, chunk = blockIdx.z;
@@ -45,9 +37,10 @@ __global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_s
     const int ln = i & 31, nt = (i >> 5) & 15, ks = i >> 9;
     const int col = chunk * kStemTcN + nt * 8 + (ln >> 2);
     const int k0 = ks * 16 + (ln & 3) * 2;
-    const __half2 p0 = __halves2half2(wt[static_cast<int64_t>(k0) * cout + col], wt[static_cast<int64_t>(k0 + 1) * cout + col]);
-    const __half2 p1 = __halves2half2(wt[static_cast<int64_t>(k0 + 8) * cout + col], wt[static_cast<int64_t>(k0 + 9) * cout + col]);
-    s_bf[ks][nt][ln] = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+    // two 16-bit weights per register (k, k + 1): pure bit packing, the same for fp16 and bf16
+    const uint32_t p0 = wt[static_cast<int64_t>(k0) * cout + col] | (static_cast<uint32_t>(wt[static_cast<int64_t>(k0 + 1) * cout + col]) << 16);
+    const uint32_t p1 = wt[static_cast<int64_t>(k0 + 8) * cout + col] | (static_cast<uint32_t>(wt[static_cast<int64_t>(k0 + 9) * cout + col]) << 16);
+    s_bf[ks][nt][ln] = make_uint2(p0, p1);
   }
   for (int i = threadIdx.x; i < kStemTcN; i += blockDim.x) s_bias[i] = bias[chunk * kStemTcN + i];
   for (int i = threadIdx.x; i < kStemTcWarps * (kStemTcN / 4) * 2; i += blockDim.x) (&s_stats[0][0][0])[i] = 0.f;
@@ -108,17 +101,15 @@ __global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_s
       }
       uint32_t a[4];
       {
-        const __half2 q0 = __floats2half2_rn(va[0][0], va[1][0]), q1 = __floats2half2_rn(va[0][1], va[1][1]);
-        const __half2 q2 = __floats2half2_rn(va[2][0], va[3][0]), q3 = __floats2half2_rn(va[2][1], va[3][1]);
-        a[0] = *reinterpret_cast<const uint32_t*>(&q0);
-        a[1] = *reinterpret_cast<const uint32_t*>(&q1);
-        a[2] = *reinterpret_cast<const uint32_t*>(&q2);
-        a[3] = *reinterpret_cast<const uint32_t*>(&q3);
+        a[0] = A16<BF16>::pack(va[0][0], va[1][0]);
+        a[1] = A16<BF16>::pack(va[0][1], va[1][1]);
+        a[2] = A16<BF16>::pack(va[2][0], va[3][0]);
+        a[3] = A16<BF16>::pack(va[2][1], va[3][1]);
       }
 #pragma unroll
       for (int nt = 0; nt < 16; ++nt) {
         const uint2 b = s_bf[ks][nt][lane];
-        stem_mma_16816(acc[nt], a, b.x, b.y);
+        mma_16816<BF16>(acc[nt], a, b.x, b.y);
       }
     }
     // epilogue: + bias, GroupNorm partial sums of the fp32 values, fp16 tile in this warp's shared memory
@@ -135,8 +126,8 @@ __global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_s
         ssum[nt] += c2 + c3;
         ssq[nt] = fmaf(c2, c2, fmaf(c3, c3, ssq[nt]));
       }
-      *reinterpret_cast<__half2*>(&s_tile[warp][g][nt * 8 + 2 * t]) = __floats2half2_rn(c0, c1);
-      *reinterpret_cast<__half2*>(&s_tile[warp][g + 8][nt * 8 + 2 * t]) = __floats2half2_rn(c2, c3);
+      *reinterpret_cast<uint32_t*>(&s_tile[warp][g][nt * 8 + 2 * t]) = A16<BF16>::pack(c0, c1);
+      *reinterpret_cast<uint32_t*>(&s_tile[warp][g + 8][nt * 8 + 2 * t]) = A16<BF16>::pack(c2, c3);
     }
     __syncwarp();
     // coalesced NHWC store: 16 pixels x 256 B, 16 lanes per pixel
@@ -191,7 +182,7 @@ __global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_s
 }  // namespace wfk
 
 extern "C" int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w, int ones_plane, const void* weight_h,
-                                   const float* bias, int cout, void* out, double* stats, int cpg, void* stream) {
+                                   const float* bias, int cout, void* out, double* stats, int cpg, int bf16, void* stream) {
   WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(in && weight_h && bias && out, "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && cin >= 1, "bad shape");
@@ -207,13 +198,19 @@ extern "C" int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w
     tpw >>= 1;
   dim3 grid((mtiles + wfk::kStemTcWarps * tpw - 1) / (wfk::kStemTcWarps * tpw), n, cout / wfk::kStemTcN);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const __half* wh = static_cast<const __half*>(weight_h);
-  __half* oh = static_cast<__half*>(out);
-  if (ksteps == 1)
-    wfk::conv3x3_stem_tc_kernel<1><<<grid, wfk::kStemTcThreads, 0, s>>>(in, cin, ones_plane, h, w, wh, bias, cout, oh, stats, cpg, tpw);
-  else if (ksteps == 2)
-    wfk::conv3x3_stem_tc_kernel<2><<<grid, wfk::kStemTcThreads, 0, s>>>(in, cin, ones_plane, h, w, wh, bias, cout, oh, stats, cpg, tpw);
-  else
-    wfk::conv3x3_stem_tc_kernel<3><<<grid, wfk::kStemTcThreads, 0, s>>>(in, cin, ones_plane, h, w, wh, bias, cout, oh, stats, cpg, tpw);
+  const uint16_t* wh = static_cast<const uint16_t*>(weight_h);
+  uint16_t* oh = static_cast<uint16_t*>(out);
+#define WFK_STEM_LAUNCH(KS, BF) \
+  wfk::conv3x3_stem_tc_kernel<KS, BF><<<grid, wfk::kStemTcThreads, 0, s>>>(in, cin, ones_plane, h, w, wh, bias, cout, oh, stats, cpg, tpw)
+  if (bf16) {
+    if (ksteps == 1) WFK_STEM_LAUNCH(1, true);
+    else if (ksteps == 2) WFK_STEM_LAUNCH(2, true);
+    else WFK_STEM_LAUNCH(3, true);
+  } else {
+    if (ksteps == 1) WFK_STEM_LAUNCH(1, false);
+    else if (ksteps == 2) WFK_STEM_LAUNCH(2, false);
+    else WFK_STEM_LAUNCH(3, false);
+  }
+#undef WFK_STEM_LAUNCH
   return wfk::launched("conv3x3_stem_tc_kernel");
 }

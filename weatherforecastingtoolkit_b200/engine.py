@@ -97,12 +97,14 @@ class _Pool:
     """Free-list of device buffers keyed by (numel, dtype): plans bind raw pointers, so buffers
     are handed out at plan-build time following the static liveness of the layer sequence."""
 
-    def __init__(self, device):
+    def __init__(self, device, adt: torch.dtype = F16):
         self.device = device
+        self.adt = adt   # default element type of activations
         self.free: Dict[Tuple[int, torch.dtype], List[torch.Tensor]] = {}
         self.all: List[torch.Tensor] = []
 
-    def get(self, shape: Sequence[int], dtype=F16) -> torch.Tensor:
+    def get(self, shape: Sequence[int], dtype=None) -> torch.Tensor:
+        dtype = self.adt if dtype is None else dtype
         n = 1
         for s in shape:
             n *= int(s)
@@ -132,9 +134,11 @@ class _Act:
 class PackedAKL:
     """fp16 / fp32 device copies of the AutoencoderKL weights in kernel layouts."""
 
-    def __init__(self, cfg: dict, sd: Dict[str, torch.Tensor], device):
+    def __init__(self, cfg: dict, sd: Dict[str, torch.Tensor], device, adt: torch.dtype = torch.float16):
         self.cfg = dict(cfg)
         self.device = device
+        self.adt = adt      # 16-bit operand / activation format: torch.float16 (default) or torch.bfloat16
+        F16 = adt           # noqa: N806 -- every ".to(F16)" below packs into the selected format
         self.t: Dict[str, torch.Tensor] = {}
         boc = list(cfg["block_out_channels"])
         self.groups = int(cfg.get("norm_num_groups", 32))
@@ -182,7 +186,7 @@ class PackedAKL:
                     if cout == 1:  # fused GroupNorm+SiLU+conv tail: [9][cin] fp32
                         self.t[mod + ".w_tap"] = w.permute(0, 2, 3, 1).reshape(9, cin).contiguous()
                 elif ".upsamplers." in mod:
-                    self.t[mod + ".w_phase"] = self._phase_weights(w)
+                    self.t[mod + ".w_phase"] = self._phase_weights(w, adt)
                 else:
                     # [9][cout][cin] fp16, slab = r*3+s
                     self.t[mod + ".w"] = w.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().to(F16)
@@ -208,7 +212,7 @@ class PackedAKL:
                 self.t[r + ".conv2.bias_sc"] = (self.t[r + ".conv2.bias"] + self.t[r + ".conv_shortcut.bias"]).contiguous()
 
     @staticmethod
-    def _phase_weights(w: torch.Tensor) -> torch.Tensor:
+    def _phase_weights(w: torch.Tensor, adt: torch.dtype = F16) -> torch.Tensor:
         """nearest-x2 upsample + conv3x3 == four 2x2 convolutions on the low-res input, one per
         output parity (a, b): rows {2y+a-1, 2y+a, 2y+a+1} // 2 collapse onto two source rows, so the
         3x3 weights are pre-summed. Returns [16 slabs = (a,b,i,j)][cout][cin] fp16."""
@@ -224,7 +228,7 @@ class PackedAKL:
                             for s in ss:
                                 acc = acc + w[:, :, r, s]
                         out[a, b, i, j] = acc
-        return out.reshape(16, cout, cin).contiguous().to(F16)
+        return out.reshape(16, cout, cin).contiguous().to(adt)
 
 
 # rows touched by upsample phase a: a=0 -> (y-1, y); a=1 -> (y, y+1)
@@ -238,8 +242,13 @@ class AKLEngine:
         self.device = torch.device(device)
         dev_index = self.device.index if self.device.index is not None else 0
         self.lib = _cabi.init(dev_index)
-        if operand_bf16:
-            raise NotImplementedError("bf16 operands fail the 1e-2 relative-L2 parity gate; fp16 only (DESIGN.md)")
+        import os
+        # Operand / activation format. fp16 is the default (it meets the 1e-2 relative-L2 parity gate with ~3x margin);
+        # bf16 -- the north-star format: same tensor-core rate and bytes, fp32 exponent range, 3 fewer mantissa bits --
+        # is selected with operand_bf16=True or WFK_OPERANDS=bf16 (measured parity: DESIGN.md section 2).
+        self.bf16 = bool(operand_bf16) or os.environ.get("WFK_OPERANDS", "fp16").lower() == "bf16"
+        self.adt = torch.bfloat16 if self.bf16 else torch.float16
+        self.dev_index = dev_index
         self.cfg = dict(cfg)
         self.boc = list(cfg["block_out_channels"])
         self.lpb = int(cfg.get("layers_per_block", 1))
@@ -253,9 +262,8 @@ class AKLEngine:
                                  f"4, 8 or 16 channels per GroupNorm group")
         if self.in_ch > 4 or self.lc > 4 or self.out_ch not in (1, 2, 4, 8) or 2 * self.lc not in (2, 4, 8):
             raise ValueError("unsupported in/out/latent channel counts for the direct edge-conv kernels")
-        self.w = PackedAKL(cfg, sd, self.device)
+        self.w = PackedAKL(cfg, sd, self.device, self.adt)
         # fused GroupNorm needs the HALO conv path (CTA pairs); both can be switched off for A/B runs
-        import os
         self.fuse_gn = (os.environ.get("WFK_FUSE_GN", "1") != "0" and os.environ.get("WFK_CONV_HALO", "1") != "0"
                         and os.environ.get("WFK_CONV_PAIR", "1") != "0")
         # (scale, shift) derived inside the conv kernel instead of a wfk_gn_table launch. Off by default: once the MMA
@@ -264,6 +272,8 @@ class AKLEngine:
         self.gn_inline = os.environ.get("WFK_GN_INLINE", "0") != "0"
         self.res_as_mma = os.environ.get("WFK_RES_AS_MMA", "1") != "0"
         self.stem_tc = os.environ.get("WFK_STEM_TC", "1") != "0"   # tensor-core stem kernels (A/B switch)
+        if self.bf16 and not (self.fuse_gn and self.stem_tc):
+            raise ValueError("bf16 operands need the default kernel set (fused GroupNorm, tensor-core stems)")
         self._plans: Dict[Tuple, "_Program"] = {}
         self._keep: List = []
 
@@ -271,8 +281,20 @@ class AKLEngine:
         """Name of a [1][c][c] fp16 identity matrix in the packed-weight table (residual add as a 1x1 MMA tap)."""
         name = f"identity{c}.w"
         if name not in self.w.t:
-            self.w.t[name] = torch.eye(c, dtype=F16, device=self.device).unsqueeze(0).contiguous()
+            self.w.t[name] = torch.eye(c, dtype=self.adt, device=self.device).unsqueeze(0).contiguous()
         return name
+
+    # ------------------------------------------------------------------ non-finite guard
+    def raise_if_nonfinite(self, sync: bool = False) -> None:
+        """Raise if a kernel of this device met inf / NaN GroupNorm statistics or model outputs (fp16 activations
+        beyond 65504 turn into that one layer later). Without ``sync`` it reports what already-completed work found
+        (free: a host read); with ``sync`` the current stream is synchronised first, so the answer covers every call
+        made so far."""
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        rc = self.lib.wfk_nonfinite_status(self.dev_index, 1)
+        if rc != 0:
+            _cabi.check(rc, "non-finite guard")
 
     # ------------------------------------------------------------------ public
     def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
@@ -306,7 +328,8 @@ class _Program:
         self.eng = eng
         self.lib = eng.lib
         self.dev = eng.device
-        self.pool = _Pool(self.dev)
+        self.pool = _Pool(self.dev, eng.adt)
+        self.bf = 1 if eng.bf16 else 0
         self.ops: List[Tuple[Callable, tuple, str]] = []
         self.plans: List[int] = []
         self.keep: List = []
@@ -336,6 +359,7 @@ class _Program:
         if out is not None and (out.shape != self.output.shape or out.dtype != torch.float32 or not out.is_contiguous()
                                 or out.device != self.output.device):
             raise ValueError(f"out must be a contiguous float32 tensor of shape {tuple(self.output.shape)} on {self.dev}")
+        self.eng.raise_if_nonfinite()      # what earlier, already completed calls found (no sync)
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.input.copy_(x)
         self.stats_arena.zero_()
@@ -404,7 +428,7 @@ class _Program:
         d.stats = _ptr(stats)
         d.out_rows, d.out_cols, d.out_sy, d.out_sx, d.ldc = out_rows, out_cols, sy, sx, ldc
         d.cpg = (d.n_total // self.eng.groups) if stats is not None else 0
-        d.operand_bf16 = 0
+        d.operand_bf16 = self.bf
 
     # ------------------------------------------------------------------ layer builders
     def gn_table(self, x: _Act, pname: str, what="gn_table") -> torch.Tensor:
@@ -526,7 +550,7 @@ class _Program:
         t = self.eng.w.t
         self._add(self.lib.wfk_groupnorm_apply,
                   (x.t.data_ptr(), x.stats.data_ptr(), t[pname + ".weight"].data_ptr(), t[pname + ".bias"].data_ptr(),
-                   n, h * w, c, self.eng.groups, GN_EPS, 1 if silu else 0, out.data_ptr()), what)
+                   n, h * w, c, self.eng.groups, GN_EPS, 1 if silu else 0, out.data_ptr(), self.bf), what)
         return out
 
     def resnet(self, x: _Act, p: str) -> _Act:
@@ -628,7 +652,7 @@ class _Program:
         self._conv_plan(d, p + ".scores", 2.0 * n * T * T * c)
         probs = self.pool.get((n, T, T))
         self._add(self.lib.wfk_softmax_rows,
-                  (scores.data_ptr(), n * T, T, 1.0 / math.sqrt(c), probs.data_ptr()), p + ".softmax")
+                  (scores.data_ptr(), n * T, T, 1.0 / math.sqrt(c), probs.data_ptr(), self.bf), p + ".softmax")
         self.pool.put(qk)
         # O = P V (+ value bias)
         o = self.pool.get((n, T, c))
@@ -678,7 +702,7 @@ class _Program:
         if eng.stem_tc and "encoder.conv_in.w_tc" in t and c0 % 128 == 0 and (c0 // eng.groups) in (4, 8, 16):
             self._add(self.lib.wfk_conv3x3_stem_tc,
                       (self.input.data_ptr(), n, cin, H, W, 0, t["encoder.conv_in.w_tc"].data_ptr(),
-                       t["encoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
+                       t["encoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups, self.bf),
                       "encoder.conv_in")
         else:
             self._add(self.lib.wfk_conv3x3_small_cin,
@@ -742,7 +766,7 @@ class _Program:
         if eng.stem_tc and "decoder.conv_in.w_tc" in t and c0 % 128 == 0 and (c0 // eng.groups) in (4, 8, 16):
             self._add(self.lib.wfk_conv3x3_stem_tc,
                       (self.input.data_ptr(), n, lc, h, w, 1, t["decoder.conv_in.w_tc"].data_ptr(),
-                       t["decoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups),
+                       t["decoder.conv_in.bias"].data_ptr(), c0, s0.data_ptr(), st.data_ptr(), c0 // eng.groups, self.bf),
                       "post_quant_conv+decoder.conv_in")
         else:
             self._add(self.lib.wfk_conv3x3_small_cin,
@@ -768,7 +792,7 @@ class _Program:
                       (x.t.data_ptr(), x.stats.data_ptr(), t["decoder.conv_norm_out.weight"].data_ptr(),
                        t["decoder.conv_norm_out.bias"].data_ptr(), n, H, W, c, eng.groups, GN_EPS,
                        t["decoder.conv_out.w_tap"].data_ptr(), float(t["decoder.conv_out.bias"][0].item()),
-                       out.data_ptr()), "decoder.conv_norm_out+silu+conv_out")
+                       out.data_ptr(), self.bf), "decoder.conv_norm_out+silu+conv_out")
             self.keep.append(x.t)
             return out
         a = self.gn(x, "decoder.conv_norm_out", what="decoder.conv_norm_out")

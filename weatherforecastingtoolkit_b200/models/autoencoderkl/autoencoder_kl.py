@@ -149,6 +149,13 @@ class AutoencoderKL(nn.Module):
         moments = self._get_engine(x.device).encode_moments(x)
         return DiagonalGaussianDistribution(moments)
 
+    def check_finite(self, sync: bool = True) -> None:
+        """Raise RuntimeError if any encode / decode of this model on its device produced inf / NaN (an fp16 activation
+        beyond 65504). ``sync=True`` synchronises the current stream first, so every call made so far is covered;
+        every encode / decode also reports, for free, what earlier completed calls found."""
+        if self._engine is not None:
+            self._engine.raise_if_nonfinite(sync=sync)
+
     def repack(self) -> None:
         """Drop the packed fp16 weights: call after writing parameters through ``.data`` (EMA swaps, manual init), which
         does not bump ``Parameter._version`` and is therefore invisible to the automatic check in ``_get_engine``."""
