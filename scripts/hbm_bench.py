@@ -35,7 +35,10 @@ def main():
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
     B, H, W = args.batch, 384, 384
+    # L2 flush: WRITE a 256 MB buffer, then READ another one -- the write alone would leave 126 MB of dirty lines whose
+    # write-back the timed kernel then pays for (it doubled the time of the 30 MB predictor pass)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_r = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
     res = {}
 
     def timeit(name, fn, nbytes):
@@ -44,6 +47,8 @@ def main():
         ts = []
         for _ in range(args.iters):
             flush.fill_(1)
+            flush_r.sum()
+            torch.cuda._sleep(200000)   # ~0.1 ms of GPU spin: the host enqueues e0 / launch / e1 behind it (no launch gap in the timing)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()

@@ -181,6 +181,10 @@ __global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __re
 __global__ void gn_table_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int hw, int c, int groups, float eps,
                                 float2* __restrict__ table, int* __restrict__ nonfinite) {
+  // programmatic dependent launch: this grid may be scheduled while the producing convolution drains (its statistics
+  // are complete and visible once the wait returns), and the consuming convolution's prologue may overlap this one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int n = blockIdx.x;
   const int cpg = c / groups;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -267,8 +271,18 @@ extern "C" int wfk_gn_table(const double* stats, const float* gamma, const float
   WFK_ENTER_STREAM(stream);
   WFK_REQUIRE(stats && gamma && beta && table, "null pointer");
   WFK_REQUIRE(n > 0 && hw > 0 && c > 0 && groups > 0 && c % groups == 0, "bad shape");
-  wfk::gn_table_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats, gamma, beta, hw, c, groups, eps,
-                                                                        static_cast<float2*>(table), wfk::nonfinite_flag());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WFK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, wfk::gn_table_kernel, stats, gamma, beta, hw, c, groups, eps,
+                                    static_cast<float2*>(table), wfk::nonfinite_flag()));
   return wfk::launched("gn_table_kernel");
 }
 

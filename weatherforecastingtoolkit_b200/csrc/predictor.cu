@@ -81,7 +81,7 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -90,7 +90,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 constexpr int kPredTcThreads = 128;   // 4 warps x 32 pixels
 
 template <int KS, int NT>   // K <= 8*KS, N == 8*NT
-__global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
+__global__ void __launch_bounds__(kPredTcThreads, 3) predict_linear_tc_kernel(
     const float* __restrict__ lat, const float* __restrict__ weight, const float* __restrict__ bias, int b, int t_in,
     int t_out, int hw, float* __restrict__ pred, float* __restrict__ tgt, double* __restrict__ loss_sums) {
   constexpr int C = 4;
@@ -141,14 +141,16 @@ __global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
     const float* lb = lat + static_cast<int64_t>(bi) * (t_in + t_out) * C * hw + p;
     // last input frame, channel t (A operand rows k = 8*ks + t and + 4 are both channel t: C == 4)
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 last_a = valid ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>((t_in - 1) * C + t) * hw)) : zero4;
+    // plane offsets as 32-bit element counts (one sequence of latents is far below 2^31 elements)
+    const unsigned uhw = static_cast<unsigned>(hw);
+    const float4 last_a = valid ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<unsigned>((t_in - 1) * C + t) * uhw)) : zero4;
     float4 xa[KS][2];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
         const int k = ks * 8 + t + 4 * hlf;
-        xa[ks][hlf] = (valid && k < K) ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>(k) * hw)) : zero4;
+        xa[ks][hlf] = (valid && k < K) ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<unsigned>(k) * uhw)) : zero4;
       }
     }
     // every other global read of the tile is issued here as well (target frames, the last input frame of the output
@@ -157,13 +159,13 @@ __global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
     float4 last_o[2], tvv[NT][2];
 #pragma unroll
     for (int e = 0; e < 2; ++e)
-      last_o[e] = valid ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>((t_in - 1) * C + ((2 * t + e) & 3)) * hw)) : zero4;
+      last_o[e] = valid ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<unsigned>((t_in - 1) * C + ((2 * t + e) & 3)) * uhw)) : zero4;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int o = nt * 8 + 2 * t + e;
-        tvv[nt][e] = (valid && o < N) ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<int64_t>(K + o) * hw)) : zero4;
+        tvv[nt][e] = (valid && o < N) ? __ldg(reinterpret_cast<const float4*>(lb + static_cast<unsigned>(K + o) * uhw)) : zero4;
       }
     float acc[2][NT][4];
 #pragma unroll
@@ -192,17 +194,26 @@ __global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
           al[mt][r] = to_tf32(v - __uint_as_float(ah[mt][r]));
         }
       }
+      // 3xTF32: the three passes of one accumulator depend on each other (~30 cycles of HMMA latency each), so the
+      // passes are the OUTER loop: 12 independent accumulators sit between two MMAs of the same one
+      uint4 bf[NT];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const uint4 bf = s_b[(ks * NT + nt) * 32 + lane];
+      for (int nt = 0; nt < NT; ++nt) bf[nt] = s_b[(ks * NT + nt) * 32 + lane];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          mma_tf32(acc[mt][nt], al[mt], bf.x, bf.y);   // lo * hi
-          mma_tf32(acc[mt][nt], ah[mt], bf.z, bf.w);   // hi * lo
-          mma_tf32(acc[mt][nt], ah[mt], bf.x, bf.y);   // hi * hi
-        }
-      }
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], al[mt], bf[nt].x, bf[nt].y);   // lo * hi
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], ah[mt], bf[nt].z, bf[nt].w);   // hi * lo
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], ah[mt], bf[nt].x, bf[nt].y);   // hi * hi
     }
+    float* pb = pred + static_cast<int64_t>(bi) * N * hw + p;
+    float* tb = tgt + static_cast<int64_t>(bi) * N * hw + p;
     if (valid) {
       // outputs o = 8*nt + 2t + e: channel (2t + e) % 4; C fragment (c0, c2 | c0', c2') = pixels 0..3 for e = 0, (c1, c3 | ..) for e = 1
 #pragma unroll
@@ -216,9 +227,9 @@ __global__ void __launch_bounds__(kPredTcThreads) predict_linear_tc_kernel(
             const float y0 = acc[0][nt][e] + bo, y1 = acc[0][nt][2 + e] + bo, y2 = acc[1][nt][e] + bo, y3 = acc[1][nt][2 + e] + bo;
             const float4 l = last_o[e];
             const float r0 = tv.x - l.x, r1 = tv.y - l.y, r2 = tv.z - l.z, r3 = tv.w - l.w;
-            const int64_t oi = (static_cast<int64_t>(bi) * N + o) * hw + p;
-            *reinterpret_cast<float4*>(pred + oi) = make_float4(y0 + l.x, y1 + l.y, y2 + l.z, y3 + l.w);
-            if (tgt != nullptr) *reinterpret_cast<float4*>(tgt + oi) = make_float4(r0 + l.x, r1 + l.y, r2 + l.z, r3 + l.w);
+            const unsigned oi = static_cast<unsigned>(o) * uhw;
+            *reinterpret_cast<float4*>(pb + oi) = make_float4(y0 + l.x, y1 + l.y, y2 + l.z, y3 + l.w);
+            if (tgt != nullptr) *reinterpret_cast<float4*>(tb + oi) = make_float4(r0 + l.x, r1 + l.y, r2 + l.z, r3 + l.w);
             const float d0 = y0 - r0, d1 = y1 - r1, d2 = y2 - r2, d3 = y3 - r3;
             loss = fmaf(d0, d0, loss);
             loss = fmaf(d1, d1, loss);
@@ -254,7 +265,7 @@ extern "C" int wfk_predict_linear(const float* lat, const float* weight, const f
   if (c == 4 && K <= 56 && N == 48 && hw % 4 == 0 && (align & 15) == 0) {
     // Path-B shape (13 -> 12 frames, 4 channels): tensor-core kernel, persistent over 128-pixel tiles
     const int64_t tiles = (static_cast<int64_t>(b) * hw + wfk::kPredTcThreads - 1) / wfk::kPredTcThreads;
-    const int64_t cap = static_cast<int64_t>(wfk::num_sms()) * 2;   // 2 CTAs per SM are resident (240 registers)
+    const int64_t cap = static_cast<int64_t>(wfk::num_sms()) * 3;   // 3 CTAs per SM are resident (<= 168 registers)
     const unsigned blocks = static_cast<unsigned>(tiles < cap ? tiles : cap);
     wfk::predict_linear_tc_kernel<7, 6><<<blocks, wfk::kPredTcThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         lat, weight, bias, b, t_in, t_out, hw, pred, tgt, loss_sums);

@@ -108,8 +108,9 @@ class LatentLinearPredictor(nn.Linear):
         tgt = torch.empty_like(pred)
         loss = torch.zeros(2, dtype=torch.float64, device=v.device)
         stream = torch.cuda.current_stream(v.device).cuda_stream
-        # algorithmic traffic: the 13 + 12 latent frames read once, 12 predicted frames written
-        with engine.timed_pass("predict_linear", 4.0 * (v.numel() + pred.numel())):
+        # algorithmic traffic: 13 input frames read + 12 predicted frames written = 25 latent frames per
+        # sequence (the kernel also reads the 12 target frames and writes them back framed: not counted)
+        with engine.timed_pass("predict_linear", 4.0 * v.numel()):
             _cabi.check(lib.wfk_predict_linear(v.data_ptr(), wt.data_ptr(), bs.data_ptr(), b, self.input_frames,
                                                self.pred_frames, c, h * w, pred.data_ptr(), tgt.data_ptr(),
                                                loss.data_ptr(), stream), "wfk_predict_linear")
