@@ -374,7 +374,9 @@ def run_b200_arm(args):
         line = {
             "metric": "forecast_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": ("bf16" if os.environ.get("WFK_OPERANDS", "fp16").lower() == "bf16" else "fp16") +
+                     " operands, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
             "config": bench_config(args, world),
             "clocks": clocks,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(host.numel()),
@@ -417,6 +419,127 @@ def run_b200_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------ BASELINE configs 0 / 3 / 4
+AUX = {
+    # name: (BASELINE.json config index, description, nominal GFLOP per frame, frame size, default frames per GPU)
+    "posaware": (0, "PosAwareAE_TF (2048-d bottleneck) encode + decode of 128x128 frames (its only valid input size)", 34.77, 128, 128),
+    "vit": (3, "AE_ViT_2048 forward, token-sequence latent [64, 512], 128x128 frames, batch 64", 4.97, 128, 64),
+    "disc": (4, "NLayerDiscriminator forward + hinge sums on 12-frame forecasts of 384x384, 16 sequences per GPU "
+                "(= batch 128 across 8 GPUs)", 14.175, 384, 192),
+}
+
+
+def run_aux_arm(args):
+    """The other model families of BASELINE.json `configs` behind the same contract: one step = one forward pass of
+    `--batch` frames per GPU (inputs resident in HBM for `value`; pinned host input + host read of the result for
+    `e2e`). Parity for these lives in tests/test_posaware.py, test_vit.py, test_discriminator.py."""
+    import torch
+    import torch.distributed as dist
+
+    from weatherforecastingtoolkit_b200 import _cabi, engine
+    from weatherforecastingtoolkit_b200 import synthetic as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.init(local_rank)
+    idx, desc, gflop, hw, default_b = AUX[args.config]
+    B = args.batch if args.batch != 32 else default_b
+    if args.config == "posaware":
+        from weatherforecastingtoolkit_b200.models.ae_64x8x8_lin import PosAwareAE_TF
+        m = PosAwareAE_TF().eval()
+        m.load_state_dict(S.fill_state_dict(m, "posaware", 0, gain=1.1))
+        fwd = lambda x: m(x)[0].mean()                                   # noqa: E731
+    elif args.config == "vit":
+        from weatherforecastingtoolkit_b200.models.ae_vit import AE_ViT_2048
+        m = AE_ViT_2048().eval()
+        m.load_state_dict(S.fill_state_dict(m, "vit", 0))
+        fwd = lambda x: m(x)[0].mean()                                   # noqa: E731
+    else:
+        from weatherforecastingtoolkit_b200.models.autoencoderkl.losses import NLayerDiscriminator
+        m = NLayerDiscriminator(input_nc=1).eval()
+        m.load_state_dict(S.make_discriminator_state_dict())
+        fwd = lambda x: m(x).mean()                                      # noqa: E731
+    m = m.to(dev)
+    g = torch.Generator().manual_seed(1 + rank)
+    host = torch.rand(B, 1, hw, hw, generator=g).pin_memory()
+    x_dev = host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            fwd(x_dev)
+        barrier()
+        timer = engine.KernelTimer()
+        engine.TIMER = timer
+        sampler = ClockSampler(local_rank)
+        l0 = _cabi.launch_count()
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = fwd(x_dev)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        engine.TIMER = None
+        launches = _cabi.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        tsum = timer.summary()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            res = float(fwd(host.to(dev, non_blocking=True)).item())
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = (float(v) for v in t.tolist())
+    if rank == 0:
+        peaks = _peaks()
+        frames = world * B * args.steps
+        fps, fps_e2e = frames / (ms / 1e3), frames / (ms_e2e / 1e3)
+        ach = tsum["nominal_flops"] / (tsum["ms"] / 1e3) / 1e12 if tsum["ms"] > 0 else 0.0
+        line = {
+            "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[{idx}]: {desc}", "batch_per_gpu": B, "frame": f"{hw}x{hw}",
+                       "l2": "activations of a step exceed the 126 MB L2" if B * hw * hw * 256 > (126 << 20) else "inputs smaller than L2; back-to-back steps",
+                       "parallelism": f"dp{world} (frame shards, no collective)"},
+            "clocks": clocks,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM / GEMM)",
+                         "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                         "traffic": None, "peak_source": peaks["which"], "launches_timed": tsum["launches"],
+                         "kernel_ms_per_step": tsum["ms"] / args.steps, "kernel_share_of_step": tsum["ms"] / ms if ms else None,
+                         "step_tflops_nominal": fps * gflop / 1e3 / world,
+                         "step_frac_of_peak": fps * gflop / 1e3 / world / peaks["tflops"],
+                         "nominal_gflop_per_frame": gflop},
+            "cpu_baseline": None, "result": res,
+        }
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,9 +551,13 @@ def main():
                     help="frames per AutoencoderKL call; 37 makes every layer's tile count a multiple of the 74 CTA pairs")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--breakdown", default=None, help="write a per-layer conv-GEMM timing table (JSON) to this path")
+    ap.add_argument("--config", default="pathb", choices=["pathb"] + sorted(AUX),
+                    help="pathb = BASELINE configs[1]/[2] (the headline metric); posaware / vit / disc = configs[0] / [3] / [4]")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.config != "pathb":
+        return run_aux_arm(args)
     return run_b200_arm(args)
 
 

@@ -148,6 +148,22 @@ int wfk_metrics(const float* pred, const float* tgt, int frames, int h, int w, c
                 int n_thresholds, int clamp01, wfk_metric_partials* out, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* The rest of pipeline/metrics.py's public surface (not used by calc_metrics' fixed sweep): any pooling window and
+ * pool_type='max' in csi / hss / crps (metrics.py:22-32, 43-50, 56-63), ensemble forecasts (pred.ndim == 6: Gaussian CRPS
+ * over n > 1 members :33-41, pred.mean(dim=1) in calc_metrics :94).  pool_kind: 0 none (scale 1), 1 avg (F.avg_pool2d:
+ * sequential row-major fp32 window sum, one division), 2 max (F.max_pool2d); stride == scale; cells = floor(h/scale) x
+ * floor(w/scale).
+ *   wfk_pooled_counts: counts [n_thresholds][4] int64 (tp, fn, fp, tn; exact), sums[0] += sum |p - t| over the pooled
+ *     cells, sums[1] += number of cells.  thresholds: HOST fp32 array.  counts / sums: DEVICE, caller-zeroed.
+ *   wfk_crps_ensemble: pred [b, n, tc, h, w], tgt [b, tc, h, w]; sums[0] += sum of the per-cell CRPS terms, sums[1] +=
+ *     cells (the reference returns their ratio).
+ *   wfk_ensemble_mean: out [b, inner] = mean over the n members of pred [b, n, inner] (fp32, members summed in order). */
+int wfk_pooled_counts(const float* pred, const float* tgt, int frames, int h, int w, int pool_kind, int scale,
+                      const float* thresholds, int n_thresholds, int clamp01, int64_t* counts, double* sums, void* stream);
+int wfk_crps_ensemble(const float* pred, const float* tgt, int b, int n, int tc, int h, int w, int pool_kind, int scale,
+                      int clamp01, double* sums, void* stream);
+int wfk_ensemble_mean(const float* pred, int b, int n, int64_t inner, int clamp01, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a3-a6, a9  Autoencoder building blocks (activations NHWC, 16 bits per value on device: fp16 by default; the
  *     entry points with a `bf16` argument / wfk_conv_desc.operand_bf16 read and write bf16 instead -- the whole chain

@@ -109,11 +109,12 @@ def _pool(x5, pool_type, scale):
 
 
 def crps(pred, target, pool_type="none", scale=1):
-    """metrics.py:18-41 for one ensemble member (pred.ndim == 5)."""
+    """metrics.py:18-41 (one member: pred.ndim == 5; ensemble: (b, n, t, c, h, w))."""
     normal = torch.distributions.Normal(0, 1)
     frac_sqrt_pi = 1 / np.sqrt(np.pi)
     eps = 1e-10
-    pred = pred.unsqueeze(1)
+    if pred.ndim == 5:
+        pred = pred.unsqueeze(1)
     b, n, t, c, h, w = pred.shape
     gt = target.reshape(b * t, c, h, w)
     pr = pred.reshape(b * n * t, c, h, w)
@@ -173,7 +174,7 @@ def calc_metrics(pred, target) -> Dict[str, float]:
     """metrics.py:86-133."""
     pred = pred.detach().clamp(0, 1)
     target = target.detach().clamp(0, 1)
-    single = pred
+    single = pred.mean(dim=1) if pred.ndim == 6 else pred
     results = {}
     results["CRPS"] = crps(pred, target, "none", 1)
     results["CRPS_4"] = crps(pred, target, "avg", 4)

@@ -185,9 +185,65 @@ def test_metrics_standalone_functions(lib):
     assert M.crps(pd, td, "avg", 4) == pytest.approx(MO.crps(p, t, "avg", 4), abs=1e-6)
     assert M.ssim(pd, td) == pytest.approx(MO.ssim(p, t), abs=2e-5)
     assert M.psnr(pd, td) == pytest.approx(MO.psnr(p, t), rel=1e-5)
-    assert [float(v) for v in MO._hit_miss_fa_cn(p, t, th)] == list(M._hit_miss_fa_cn(pd, td, th))
-    with pytest.raises(NotImplementedError):
-        M.csi(pd, td, th, "max", 4)
+    got4 = M._hit_miss_fa_cn(pd, td, th)
+    assert all(isinstance(v, torch.Tensor) and v.ndim == 0 and v.dtype == torch.float32 and v.is_cuda for v in got4)
+    assert [float(v) for v in MO._hit_miss_fa_cn(p, t, th)] == [float(v) for v in got4]
+    with pytest.raises(ValueError):
+        M.csi(pd, td, th, "median", 4)
+
+
+def test_metrics_generic_pools_and_ensembles_vs_reference_golden(lib):
+    """pool_type='max', any scale, ensemble forecasts: the generic kernels against values computed by the UNMODIFIED
+    reference module (tests/golden/make_golden_metrics_extra.py). CSI / HSS bit-exact (exact counts below 2**24 are
+    what the reference's float32 sums hold too), CRPS to float32 rounding."""
+    import json
+    import os
+    import sys
+
+    from conftest import GOLDEN
+    from weatherforecastingtoolkit_b200 import metrics as M
+    sys.path.insert(0, GOLDEN)
+    from make_golden_metrics_extra import THS, inputs
+    with open(os.path.join(GOLDEN, "metrics_extra_golden.json")) as f:
+        gold = json.load(f)
+    p, t, ens, gt = inputs()
+    pd, td, ed, gd = p.to(DEV), t.to(DEV), ens.to(DEV), gt.to(DEV)
+    for row in gold["pooled"]:
+        pool, scale = row["pool_type"], row["scale"]
+        assert M.crps(pd, td, pool, scale) == pytest.approx(row["crps"], rel=2e-6), (pool, scale)
+        for th in THS:
+            assert M.csi(pd, td, th, pool, scale) == row[f"csi_{th:.6f}"], (pool, scale, th)
+            assert M.hss(pd, td, th, pool, scale) == row[f"hss_{th:.6f}"], (pool, scale, th)
+    for row in gold["crps_ensemble"]:
+        assert M.crps(ed, gd, row["pool_type"], row["scale"]) == pytest.approx(row["crps"], rel=2e-5), row
+    assert [float(v) for v in M._hit_miss_fa_cn(pd, td, THS[1])] == gold["hit_miss_fa_cn"]
+    got = M.calc_metrics(ed, gd)
+    want = gold["ensemble_calc_metrics"]
+    assert list(got) == list(want)
+    for k, v in want.items():
+        if k.startswith(("CSI", "HSS", "paper_CSI", "paper_HSS")):
+            assert got[k] == v, k          # ensemble mean bit-identical to torch's pred.mean(dim=1), then exact counts
+        elif "SSIM" in k:
+            assert got[k] == pytest.approx(v, abs=2e-5), k
+        else:
+            assert got[k] == pytest.approx(v, rel=2e-5), k
+    # the ensemble mean itself
+    assert torch.equal(M.ensemble_mean(ed, clamp=True).cpu(), ens.clamp(0, 1).mean(dim=1))
+
+
+def test_metric_accumulator_reference_semantics(lib):
+    from weatherforecastingtoolkit_b200 import metrics as M
+    p, t = metric_case_inputs("vil_2x12x384")
+    acc = M.MetricAccumulator(reference_semantics=True)
+    per = []
+    for i in range(2):
+        acc.update(p[i:i + 1].to(DEV), t[i:i + 1].to(DEV))
+        per.append(M.calc_metrics(p[i:i + 1].to(DEV), t[i:i + 1].to(DEV)))
+    got = acc.compute()
+    for k in per[0]:
+        assert got[k] == pytest.approx((per[0][k] + per[1][k]) / 2, rel=1e-12, abs=1e-15), k
+    ratio_of_sums = M.calc_metrics(p.to(DEV), t.to(DEV))
+    assert got["CSI_3"] != ratio_of_sums["CSI_3"]       # mean of per-batch ratios != ratio of summed counts
 
 
 def test_metrics_edge_cases(lib):

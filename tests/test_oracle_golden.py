@@ -111,3 +111,29 @@ def test_stage_vil_formula():
     want = (np.arange(256, dtype=np.float32) * scale).reshape(1, 16, 16, 1)
     assert np.array_equal(x.numpy(), want)
     assert scale.view(np.uint32) == 0x3B808081
+
+
+def test_metrics_oracle_vs_reference_extra_golden():
+    """pool_type='max', arbitrary scale and ensemble forecasts (tests/golden/make_golden_metrics_extra.py: values from
+    the unmodified reference module)."""
+    import json
+    import os
+    import sys
+
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from make_golden_metrics_extra import THS, inputs
+    with open(os.path.join(GOLDEN, "metrics_extra_golden.json")) as f:
+        gold = json.load(f)
+    p, t, ens, gt = inputs()
+    for row in gold["pooled"]:
+        pool, scale = row["pool_type"], row["scale"]
+        assert MO.crps(p, t, pool, scale) == pytest.approx(row["crps"], rel=1e-6)
+        for th in THS:
+            assert MO.csi(p, t, th, pool, scale) == row[f"csi_{th:.6f}"]
+            assert MO.hss(p, t, th, pool, scale) == row[f"hss_{th:.6f}"]
+    for row in gold["crps_ensemble"]:
+        assert MO.crps(ens, gt, row["pool_type"], row["scale"]) == pytest.approx(row["crps"], rel=1e-6)
+    got = MO.calc_metrics(ens, gt)
+    for k, v in gold["ensemble_calc_metrics"].items():
+        assert got[k] == pytest.approx(v, rel=1e-6, abs=1e-7), k

@@ -90,6 +90,11 @@ _PROTOTYPES = {
     "wfk_metrics_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "wfk_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
                               C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wfk_pooled_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wfk_crps_ensemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_void_p]),
+    "wfk_ensemble_mean": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "wfk_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
     "wfk_conv_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wfk_conv_plan_destroy": (None, [C.c_void_p]),

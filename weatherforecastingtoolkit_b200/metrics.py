@@ -14,6 +14,15 @@ reports the score of the GLOBAL batch (sum of counts, not the reference's mean o
 Numerics: counts are exact integers (the reference's float32 sums round above 2**24, hazard H1);
 ratios are then formed with the reference's float32 operation order, so CSI / HSS are bit-identical
 to the reference whenever its own counts are exact. There is no CPU path: inputs must be CUDA tensors.
+
+Coverage of the reference surface: ``calc_metrics`` and the fixed sweep it runs (pools none / avg 4 / avg 16, one
+member) go through the fused kernel; every other combination the reference functions accept -- ``pool_type='max'``,
+any ``scale``, ensemble forecasts ``pred.ndim == 6`` (Gaussian CRPS over n members, ``pred.mean(dim=1)`` for the
+categorical scores) -- goes through the generic kernels of ``csrc/metrics_generic.cu``. Differences from the reference
+that remain: inputs must be (.., 1, h, w) CUDA tensors with h, w >= 11 for SSIM; ``_hit_miss_fa_cn`` returns the EXACT
+counts as float32 0-dim tensors (the reference's float32 sums are rounded above 2**24); ``MetricAccumulator`` and
+``process_group`` report the ratio of summed counts, where Lightning's ``log_dict(on_epoch=True, sync_dist=True)``
+averages per-batch / per-rank ratios (``reference_semantics=True`` on the accumulator reproduces the latter).
 """
 from __future__ import annotations
 
@@ -89,7 +98,7 @@ def _as_frames(x: torch.Tensor) -> torch.Tensor:
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         raise RuntimeError("weatherforecastingtoolkit_b200.metrics needs CUDA tensors (no CPU fallback)")
     if x.ndim == 6:
-        raise NotImplementedError("ensemble inputs (ndim 6) are outside the Path-B scoring path")
+        raise ValueError("ensemble forecasts (b, n, t, 1, h, w) are reduced by the caller (calc_metrics / crps)")
     if x.ndim not in (4, 5) or x.shape[-3] != 1:
         raise ValueError(f"expected (b, t, 1, h, w) or (n, 1, h, w), got {tuple(x.shape)}")
     return x.detach().to(torch.float32).contiguous().view(-1, x.shape[-2], x.shape[-1])
@@ -164,18 +173,25 @@ class MetricAccumulator:
     """Epoch-level running scores: the device-resident partials of every ``update`` are added on the
     GPU without a host sync; ``compute`` does one all-reduce (optional) and one D2H copy and returns the scores of
     everything seen since the last ``reset`` -- a ratio of sums over the epoch, where the reference's
-    ``log_dict(on_epoch=True)`` (pipeline/helpers.py:151-153) averages per-batch ratios."""
+    ``log_dict(on_epoch=True)`` (pipeline/helpers.py:151-153) averages per-batch ratios.
+    ``reference_semantics=True`` keeps the per-batch partials as well and ``compute`` returns the MEAN OF THE PER-BATCH
+    SCORES (equal batch weights), i.e. the number Lightning logs for the reference; the two differ whenever the
+    batches' event counts differ."""
 
-    def __init__(self, thresholds: Sequence[float] = THRESHOLDS):
+    def __init__(self, thresholds: Sequence[float] = THRESHOLDS, reference_semantics: bool = False):
         self.thresholds = list(thresholds)
+        self.reference_semantics = bool(reference_semantics)
         self._acc: Optional[torch.Tensor] = None
+        self._per_batch: list = []
         self.batches = 0
 
     def reset(self) -> None:
-        self._acc, self.batches = None, 0
+        self._acc, self.batches, self._per_batch = None, 0, []
 
     def update(self, pred: torch.Tensor, target: torch.Tensor) -> None:
         part = metric_partials_device(pred, target, self.thresholds, clamp=True)
+        if self.reference_semantics:
+            self._per_batch.append(part)
         self._acc = part if self._acc is None else _add_device(self._acc, part)
         self.batches += 1
 
@@ -188,6 +204,21 @@ class MetricAccumulator:
         return _to_host(dev_struct, len(self.thresholds))
 
     def compute(self, extended: bool = False, process_group=None) -> Dict[str, float]:
+        if self.reference_semantics:
+            if not self._per_batch:
+                raise RuntimeError("MetricAccumulator.compute() before any update()")
+            host = torch.stack(self._per_batch).cpu().numpy()          # one D2H copy for the whole epoch
+            per = [scores_from_partials(MetricPartials(h[:_N_INT], h[_N_INT:].view(np.float64), len(self.thresholds)),
+                                        extended=extended) for h in host]
+            res = {k: float(np.mean([d[k] for d in per])) for k in per[0]}
+            if process_group is not None:                               # sync_dist=True: mean over ranks of the means
+                import torch.distributed as dist
+                keys = list(res)
+                v = torch.tensor([res[k] for k in keys], dtype=torch.float64, device=self._per_batch[0].device)
+                dist.all_reduce(v, op=dist.ReduceOp.SUM, group=None if process_group is True else process_group)
+                v /= dist.get_world_size(None if process_group is True else process_group)
+                res = {k: float(x) for k, x in zip(keys, v.tolist())}
+            return res
         return scores_from_partials(self.partials(process_group), extended=extended)
 
 
@@ -249,44 +280,136 @@ def scores_from_partials(mp: MetricPartials, extended: bool = False) -> Dict[str
     return res
 
 
+# ------------------------------------------------------------------ generic (non-sweep) paths
+_POOL_KIND = {"none": 0, "avg": 1, "max": 2}
+
+
+def _pool_args(pool_type: str, scale: int):
+    if pool_type not in _POOL_KIND:
+        # the reference silently skips pooling for an unknown pool_type (metrics.py:27-32 / 44); refuse instead
+        raise ValueError(f"pool_type={pool_type!r}: expected 'none', 'avg' or 'max'")
+    kind = _POOL_KIND[pool_type]
+    scale = int(scale)
+    if kind == 0:
+        return 0, 1          # csi / hss / crps ignore `scale` without pooling (metrics.py:27-32, 44)
+    if scale < 1:
+        raise ValueError("scale must be >= 1")
+    return kind, scale
+
+
+def _fused(pool_type: str, scale: int) -> Optional[int]:
+    """Index of the pool inside the fused kernel's partials, or None when the generic kernel has to serve it."""
+    if pool_type == "none":
+        return 0
+    if pool_type == "avg" and int(scale) in _POOL_INDEX:
+        return _POOL_INDEX[int(scale)]
+    return None
+
+
+def pooled_counts(pred, target, thresholds: Sequence[float], pool_type: str = "none", scale: int = 1, clamp: bool = False):
+    """Exact (tp, fn, fp, tn) per threshold and the sum of |p - t| over the pooled cells for ANY pooling the reference
+    accepts (metrics.py:43-50): returns (int64 array [n_thresholds, 4], abs_sum, n_cells)."""
+    p, t = _as_frames(pred), _as_frames(target)
+    if p.shape != t.shape:
+        raise ValueError("pred and target shapes differ")
+    kind, scale = _pool_args(pool_type, scale)
+    dev = p.device
+    lib = _cabi.init(dev.index if dev.index is not None else 0)
+    frames, h, w = p.shape
+    thr = (C.c_float * max(len(thresholds), 1))(*[float(np.float32(th)) for th in thresholds])
+    counts = torch.zeros(max(len(thresholds), 1) * 4, dtype=torch.int64, device=dev)
+    sums = torch.zeros(2, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _cabi.check(lib.wfk_pooled_counts(p.data_ptr(), t.data_ptr(), frames, h, w, kind, scale, thr, len(thresholds),
+                                      1 if clamp else 0, counts.data_ptr(), sums.data_ptr(), stream), "wfk_pooled_counts")
+    s = sums.cpu().numpy()
+    return counts.cpu().numpy().reshape(-1, 4)[: len(thresholds)], float(s[0]), int(s[1])
+
+
+def ensemble_mean(pred: torch.Tensor, clamp: bool = False) -> torch.Tensor:
+    """``pred.mean(dim=1)`` of an ensemble forecast (b, n, t, c, h, w) (metrics.py:94), members summed in order."""
+    if not pred.is_cuda or pred.ndim != 6:
+        raise ValueError("expected a CUDA tensor (b, n, t, c, h, w)")
+    x = pred.detach().to(torch.float32).contiguous()
+    b, n = x.shape[:2]
+    out = torch.empty((b,) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    lib = _cabi.init(x.device.index if x.device.index is not None else 0)
+    _cabi.check(lib.wfk_ensemble_mean(x.data_ptr(), b, n, out[0].numel(), 1 if clamp else 0, out.data_ptr(),
+                                      torch.cuda.current_stream(x.device).cuda_stream), "wfk_ensemble_mean")
+    return out
+
+
+def _crps_ensemble(pred: torch.Tensor, target: torch.Tensor, pool_type: str, scale: int, clamp: bool) -> float:
+    if not (pred.is_cuda and target.is_cuda):
+        raise RuntimeError("weatherforecastingtoolkit_b200.metrics needs CUDA tensors (no CPU fallback)")
+    x = pred.detach().to(torch.float32).contiguous()
+    g = target.detach().to(torch.float32).contiguous()
+    b, n, tt, c, h, w = x.shape
+    if g.shape != (b, tt, c, h, w):
+        raise ValueError(f"target {tuple(g.shape)} does not match the ensemble {tuple(x.shape)}")
+    kind, scale = _pool_args(pool_type, scale)
+    lib = _cabi.init(x.device.index if x.device.index is not None else 0)
+    sums = torch.zeros(2, dtype=torch.float64, device=x.device)
+    _cabi.check(lib.wfk_crps_ensemble(x.data_ptr(), g.data_ptr(), b, n, tt * c, h, w, kind, scale, 1 if clamp else 0,
+                                      sums.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream), "wfk_crps_ensemble")
+    s = sums.cpu().numpy()
+    return float(np.float32(s[0] / s[1]))
+
+
 # ------------------------------------------------------------------ reference-named entry points
 def calc_metrics(pred, target, extended: bool = False, process_group=None) -> Dict[str, float]:
-    """pred and target shape == (b, t, c, h, w); clamps to [0, 1] like the reference (metrics.py:86-133)."""
+    """pred and target shape == (b, t, c, h, w); clamps to [0, 1] like the reference (metrics.py:86-133). An ensemble
+    forecast (b, n, t, c, h, w) is scored like the reference does: CRPS over the members, everything else on the
+    ensemble mean (metrics.py:94)."""
+    if isinstance(pred, torch.Tensor) and pred.ndim == 6:
+        if process_group is not None:
+            raise NotImplementedError("ensemble CRPS is not additive over ranks: reduce per rank")
+        single = ensemble_mean(pred, clamp=True)
+        res = scores_from_partials(metric_partials(single, target, THRESHOLDS, clamp=True), extended=extended)
+        res["CRPS"] = _crps_ensemble(pred, target, "none", 1, True)
+        res["CRPS_4"] = _crps_ensemble(pred, target, "avg", 4, True)
+        res["CRPS_16"] = _crps_ensemble(pred, target, "avg", 16, True)
+        res["paper_CRPS"] = res["CRPS"]
+        return res
     return scores_from_partials(metric_partials(pred, target, THRESHOLDS, clamp=True, process_group=process_group),
                                 extended=extended)
 
 
-def _pool_idx(pool_type: str, scale: int) -> int:
-    if pool_type == "none" or scale == 1:
-        return 0
-    if pool_type == "avg" and scale in _POOL_INDEX:
-        return _POOL_INDEX[scale]
-    raise NotImplementedError(f"pool_type={pool_type!r} scale={scale}: the fused kernel implements the pools "
-                              "calc_metrics uses (none, avg 4, avg 16)")
-
-
 def _hit_miss_fa_cn(pred, target, threshold):
-    """Exact integer (tp, fn, fp, tn) as float64 scalars (reference returns float32 sums, :9-16)."""
-    mp = metric_partials(pred, target, [threshold], clamp=False)
-    c = mp.counts[0, 0]
-    return float(c[0]), float(c[1]), float(c[2]), float(c[3])
+    """(tp, fn, fp, tn) as 0-dim float32 tensors on the input device, like the reference (:9-16) -- but holding the EXACT
+    counts rounded once to float32, where the reference's float32 sums accumulate rounding above 2**24."""
+    c, _, _ = pooled_counts(pred, target, [threshold], "none", 1)
+    return tuple(torch.tensor(float(v), dtype=torch.float32, device=pred.device) for v in c[0])
+
+
+def _counts_for(pred, target, threshold, pool_type, scale):
+    fi = _fused(pool_type, scale)
+    if fi is not None:
+        return metric_partials(pred, target, [threshold], clamp=False).counts[fi, 0]
+    return pooled_counts(pred, target, [threshold], pool_type, scale)[0][0]
 
 
 def csi(pred, target, threshold, pool_type="none", scale=1):
-    mp = metric_partials(pred, target, [threshold], clamp=False)
-    return _csi_from_counts(mp.counts[_pool_idx(pool_type, scale), 0])
+    return _csi_from_counts(_counts_for(pred, target, threshold, pool_type, scale))
 
 
 def hss(pred, target, threshold, pool_type="none", scale=1):
-    mp = metric_partials(pred, target, [threshold], clamp=False)
-    return _hss_from_counts(mp.counts[_pool_idx(pool_type, scale), 0])
+    return _hss_from_counts(_counts_for(pred, target, threshold, pool_type, scale))
 
 
 def crps(pred, target, pool_type="none", scale=1):
-    """One ensemble member: CRPS == mean |pred - target| (metrics.py:18-41 with n == 1)."""
-    mp = metric_partials(pred, target, [0.5], clamp=False)
-    i = _pool_idx(pool_type, scale)
-    return float(mp.abs_sum[i] / mp.n_elems[i])
+    """metrics.py:18-41. One member (pred.ndim == 5): CRPS == mean |pred - target| (to ~1e-10); an ensemble
+    (b, n, t, c, h, w): the Gaussian closed form over the member mean / std."""
+    if isinstance(pred, torch.Tensor) and pred.ndim == 6 and pred.shape[1] > 1:
+        return _crps_ensemble(pred, target, pool_type, scale, False)
+    if isinstance(pred, torch.Tensor) and pred.ndim == 6:
+        pred = pred[:, 0]
+    fi = _fused(pool_type, scale)
+    if fi is not None:
+        mp = metric_partials(pred, target, [0.5], clamp=False)
+        return float(mp.abs_sum[fi] / mp.n_elems[fi])
+    _, abs_sum, cells = pooled_counts(pred, target, [], pool_type, scale)
+    return float(abs_sum / cells)
 
 
 def ssim(pred, target):
