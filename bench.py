@@ -480,8 +480,7 @@ def run_aux_arm(args):
         for _ in range(max(args.warmup, 1)):
             fwd(x_dev)
         barrier()
-        timer = engine.KernelTimer()
-        engine.TIMER = timer
+        # ---- timed region 1: inputs resident in HBM (the programs replay their CUDA graphs)
         sampler = ClockSampler(local_rank)
         l0 = _cabi.launch_count()
         if rank == 0:
@@ -494,10 +493,21 @@ def run_aux_arm(args):
         e1.record()
         barrier()
         clocks = sampler.stop() if rank == 0 else None
-        engine.TIMER = None
-        launches = _cabi.launch_count() - l0
         ms = e0.elapsed_time(e1)
+        # ---- kernel-time accounting for the roofline leg: the same steps launched eagerly with CUDA events around every
+        # tensor-core launch (not part of `value`)
+        timer = engine.KernelTimer()
+        engine.TIMER = timer
+        l1 = _cabi.launch_count()
+        for _ in range(args.steps):
+            fwd(x_dev)
+        barrier()
+        engine.TIMER = None
+        # kernels of the timed region: graph replays do not pass through the C ABI counter, the eager pass launches the
+        # same op list
+        launches = max(_cabi.launch_count() - l1, _cabi.launch_count() - l0 - (_cabi.launch_count() - l1))
         tsum = timer.summary()
+        # ---- timed region 2: end to end, pinned host input, host read of the result
         barrier()
         e0.record()
         for _ in range(args.steps):

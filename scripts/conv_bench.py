@@ -17,7 +17,8 @@ dev = torch.device("cuda:0")
 def harness(eng, n):
     self = object.__new__(_Program)
     self.eng, self.lib, self.dev = eng, eng.lib, eng.device
-    self.pool = _Pool(self.dev)
+    self.pool = _Pool(self.dev, eng.adt)
+    self.bf = 1 if eng.bf16 else 0
     self.ops, self.plans, self.keep = [], [], []
     self.n = n
     self.stats_arena = torch.zeros(8, n, eng.groups, 2, dtype=torch.float64, device=self.dev)
@@ -71,7 +72,7 @@ def main():
             hs.upsample(_Act(x, None), "tmp.w", bias)
         elif mode == "down":
             hs.downsample(_Act(x, None), "tmp.w", bias)
-        fn, args, what, flops = hs.ops[0]
+        fn, args, what, flops, *_ = hs.ops[0]
         for _ in range(2):
             _cabi.check(fn(*args, stream), what)
         torch.cuda.synchronize()

@@ -41,6 +41,13 @@ class NetProgram:
         self.ops: List[Tuple[Callable, tuple, str, float]] = []
         self.plans: List = []
         self.keep: List = []
+        # These networks are ~100-250 short launches per forward (3 ms for a 64-frame ViT batch): launch-bound. After
+        # one eager run (which also sets the kernels' shared-memory attributes) the whole op list is captured into a
+        # CUDA graph and replayed; WFK_CUDA_GRAPH=0 keeps the eager path (A/B switch, identical results).
+        import os
+        self.use_graph = os.environ.get("WFK_CUDA_GRAPH", "1") != "0"
+        self._graph = None
+        self._eager_runs = 0
 
     def __del__(self):
         try:
@@ -54,6 +61,28 @@ class NetProgram:
         self.ops.append((fn, tuple(args), what, float(flops)))
 
     def run(self):
+        if engine.TIMER is None and self.use_graph:
+            if self._graph is not None:
+                self._graph.replay()
+                return
+            if self._eager_runs >= 1:
+                try:
+                    torch.cuda.synchronize(self.dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._run_eager()
+                    self._graph = g
+                    g.replay()
+                    return
+                except Exception as e:   # capture is an optimisation: fall back to the eager launches
+                    import warnings
+                    warnings.warn(f"CUDA graph capture failed ({e}); running eagerly")
+                    self.use_graph = False
+                    torch.cuda.synchronize(self.dev)
+        self._eager_runs += 1
+        self._run_eager()
+
+    def _run_eager(self):
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         timer = engine.TIMER
         for fn, args, what, flops in self.ops:
