@@ -53,3 +53,40 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert mine["e2e"]["value"] / d["value"] > 100      # the headline ratio the driver computes
+
+
+def test_round2_line_has_honest_roofline_and_secondary_passes():
+    d = _line("r2_bench_1gpu.json")
+    r = d["roofline"]
+    assert 0.5 < r["frac_executed"] < r["frac"] <= 1.0          # executed MMA work < nominal (sub-pixel upsample)
+    assert r["executed_tflops"] == pytest.approx(r["frac_executed"] * r["peak"], rel=1e-9)
+    assert r["step_frac_of_peak_executed"] < r["step_frac_of_peak"]
+    for key in ("n256", "n128"):
+        tr = r["traffic_ncu"][key]
+        assert os.path.exists(os.path.join(ROOT, tr["source"])) and tr["dram_bytes"] > 1e8
+        assert 40 < tr["tensor_pipe_pct_elapsed"] < 100
+    assert r["traffic"] == r["traffic_ncu"]["n256"]["dram_bytes"]
+    sec = r["secondary"]
+    assert set(sec) == {"stage_vil", "predict_linear", "metrics"}
+    for name, s in sec.items():
+        assert s["bound"] == "hbm" and 0 < s["frac"] < 1.05 and s["gbs"] == pytest.approx(s["frac"] * r["hbm_peak_gbs"], rel=1e-9)
+    assert sec["stage_vil"]["algorithmic_bytes_per_launch"] == 32 * 25 * 384 * 384 * 5
+    assert sec["predict_linear"]["algorithmic_bytes_per_launch"] == 32 * 921600
+    assert sec["metrics"]["algorithmic_bytes_per_launch"] == 32 * 12 * 1179648
+    assert d["parity_check"] is None                                   # single rank
+    ref = _line("r2_bench_reference_arm.json")
+    assert ref["config"] == d["config"] and ref["impl"] == "reference"
+
+
+def test_round2_two_gpu_line_checks_the_reduction_on_device():
+    d = _line("r2_bench_2gpu.json")
+    assert d["n_gpus"] == 2 and d["parity_check"] == "ok"
+    assert d["value"] == pytest.approx(2 * 12 * 32 / (d["ms_per_step"] * 1e-3), rel=1e-6)
+
+
+@pytest.mark.parametrize("cfg", ["posaware", "vit", "disc"])
+def test_round2_aux_config_lines(cfg):
+    d = _line(f"r2_bench_config_{cfg}.json")
+    assert d["unit"] == "frames/s" and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
+    assert "BASELINE configs[" in d["config"]["workload"] and "model" not in d["config"]
+    assert d["roofline"]["bound"] == "tensor" and 0 < d["roofline"]["step_frac_of_peak"] < 1

@@ -46,6 +46,31 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_experiments(verbose: bool = False) -> Path:
+    """libwfk_b200_exp.so: the same sources with -DWFK_EXPERIMENTS (timing experiments that produce WRONG results by
+    design: operand traffic removed, stores skipped, fewer CTA pairs). Never loaded by the package; select it for a
+    scripts/ run with WFK_LIB_PATH."""
+    nvcc = _nvcc()
+    objdir = PKG / "build_exp"
+    objdir.mkdir(exist_ok=True)
+    out = PKG / "libwfk_b200_exp.so"
+    procs, objs = [], []
+    for src in _sources():
+        obj = objdir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-DWFK_EXPERIMENTS", "-I", str(PKG.parent / "include"), "-c", str(src), "-o", str(obj)]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    for src, pr in procs:
+        o, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name}:\n{o}")
+    r = subprocess.run([nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                        "-o", str(out), *objs], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     dig = _digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == dig:
@@ -78,5 +103,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(p)
+    if "--experiments" in sys.argv:
+        print(build_experiments(verbose="-v" in sys.argv))
+    else:
+        p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(p)

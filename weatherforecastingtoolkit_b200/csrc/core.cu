@@ -35,11 +35,20 @@ void DeviceScope::enter(int device) {
 
 DeviceScope DeviceScope::from_stream(void* stream) {
   int device = -1;
-  // the legacy / per-thread default streams report the calling thread's current device
-  cudaError_t e = cudaStreamGetDevice(static_cast<cudaStream_t>(stream), &device);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
+  cudaError_t e;
+  // cudaStreamGetDevice is illegal on a stream that is being captured into a CUDA graph (it invalidates the capture,
+  // probed in scripts/probes/capture_api_probe.cu): a capturing thread's current device is the stream's device
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (stream != nullptr && cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &cap) == cudaSuccess &&
+      cap != cudaStreamCaptureStatusNone) {
     e = cudaGetDevice(&device);
+  } else {
+    // the legacy / per-thread default streams report the calling thread's current device
+    e = cudaStreamGetDevice(static_cast<cudaStream_t>(stream), &device);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaGetDevice(&device);
+    }
   }
   if (e != cudaSuccess) device = -1;
   return DeviceScope(device);

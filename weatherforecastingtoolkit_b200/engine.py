@@ -272,6 +272,7 @@ class AKLEngine:
         self.gn_inline = os.environ.get("WFK_GN_INLINE", "0") != "0"
         self.res_as_mma = os.environ.get("WFK_RES_AS_MMA", "1") != "0"
         self.stem_tc = os.environ.get("WFK_STEM_TC", "1") != "0"   # tensor-core stem kernels (A/B switch)
+        self.attn_group = int(os.environ.get("WFK_ATTN_GROUP", "0"))   # frames per attention group (0: all frames at once)
         if self.bf16 and not (self.fuse_gn and self.stem_tc):
             raise ValueError("bf16 operands need the default kernel set (fused GroupNorm, tensor-core stems)")
         self._plans: Dict[Tuple, "_Program"] = {}
@@ -638,33 +639,41 @@ class _Program:
         self._epilogue(d, None, None, vt, None, None, 1, c, T)
         self._conv_plan(d, p + ".value^T", 2.0 * n * T * c * c)
         self.pool.put(a)
-        # scores = Q K^T (fp32), scale folded into the softmax
-        scores = self.pool.get((n, T, T), torch.float32)
-        d = ConvDesc()
-        self._view_nhwc(d.a[0], qk, n, 1, T, c, pitch_c=2 * c)
-        kview = qk.view(-1)[c:]
-        self._view_w(d.b[0], kview, c, T, n, pitch_k=2 * c, slab_stride=T * 2 * c * 2)
-        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, 1, T, T
-        d.num_phases, d.taps_per_phase = 1, 1
-        d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
-        d.a_frame_mul, d.b_frame_mul = 1, 1
-        self._epilogue(d, None, None, None, scores, None, 1, T, T)
-        self._conv_plan(d, p + ".scores", 2.0 * n * T * T * c)
-        probs = self.pool.get((n, T, T))
-        self._add(self.lib.wfk_softmax_rows,
-                  (scores.data_ptr(), n * T, T, 1.0 / math.sqrt(c), probs.data_ptr(), self.bf), p + ".softmax")
-        self.pool.put(qk)
-        # O = P V (+ value bias)
+        # scores = Q K^T (fp32) -> row softmax -> O = P V (+ value bias). The chain can run in groups of `ag` frames so
+        # that the fp32 scores (21 MB per frame at 2304 tokens) and the probabilities of a group stay in the 126 MB L2
+        # instead of streaming 63 MB per frame through HBM (WFK_ATTN_GROUP). Measured on B200 (same box, bench.py):
+        # all 37 frames at once 314.7 frames/s; groups of 4 / 3 / 2 / 1 frames 312.8 / 311.0 / 309.5 / 303.2 -- the extra
+        # launches and the partial last wave of 162-tile GEMMs cost more than the HBM traffic they save, so the default
+        # is one group.
         o = self.pool.get((n, T, c))
-        d = ConvDesc()
-        self._view_nhwc(d.a[0], probs, n, 1, T, T)
-        self._view_w(d.b[0], vt, T, c, n)
-        d.n_frames, d.tile_h, d.tile_w, d.n_total = n, 1, T, c
-        d.num_phases, d.taps_per_phase = 1, 1
-        d.taps[0] = Tap(0, 0, 0, 0, 0, 0, (T + 63) // 64, 0)
-        d.a_frame_mul, d.b_frame_mul = 1, 1
-        self._epilogue(d, t[p + ".value.bias"], None, o, None, None, 1, T, c)
-        self._conv_plan(d, p + ".pv", 2.0 * n * T * T * c)
+        ag = max(1, min(n, self.eng.attn_group if self.eng.attn_group > 0 else n))
+        scores = self.pool.get((ag, T, T), torch.float32)
+        probs = self.pool.get((ag, T, T))
+        esz = 2
+        for g0 in range(0, n, ag):
+            ng = min(ag, n - g0)
+            d = ConvDesc()
+            self._view_nhwc(d.a[0], qk[g0:], ng, 1, T, c, pitch_c=2 * c)
+            kview = qk[g0:].reshape(-1)[c:]
+            self._view_w(d.b[0], kview, c, T, ng, pitch_k=2 * c, slab_stride=T * 2 * c * esz)
+            d.n_frames, d.tile_h, d.tile_w, d.n_total = ng, 1, T, T
+            d.num_phases, d.taps_per_phase = 1, 1
+            d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
+            d.a_frame_mul, d.b_frame_mul = 1, 1
+            self._epilogue(d, None, None, None, scores, None, 1, T, T)
+            self._conv_plan(d, p + ".scores", 2.0 * ng * T * T * c)
+            self._add(self.lib.wfk_softmax_rows,
+                      (scores.data_ptr(), ng * T, T, 1.0 / math.sqrt(c), probs.data_ptr(), self.bf), p + ".softmax")
+            d = ConvDesc()
+            self._view_nhwc(d.a[0], probs, ng, 1, T, T)
+            self._view_w(d.b[0], vt[g0:], T, c, ng)
+            d.n_frames, d.tile_h, d.tile_w, d.n_total = ng, 1, T, c
+            d.num_phases, d.taps_per_phase = 1, 1
+            d.taps[0] = Tap(0, 0, 0, 0, 0, 0, (T + 63) // 64, 0)
+            d.a_frame_mul, d.b_frame_mul = 1, 1
+            self._epilogue(d, t[p + ".value.bias"], None, o[g0:], None, None, 1, T, c)
+            self._conv_plan(d, p + ".pv", 2.0 * ng * T * T * c)
+        self.pool.put(qk)
         self.pool.put(scores)
         self.pool.put(probs)
         self.pool.put(vt)
