@@ -108,6 +108,10 @@ struct ConvKernelParams {
   const float* scale2;
   const float* shift2;
   uint32_t idesc;
+  // Cout = 128 HALO kernel (MB = 2): 16-bit output through TMA stores. (c, x, y, frame) view of the NHWC output, box
+  // 32 channels x 8 x 4 pixels = one epilogue warp's chunk, 64-byte swizzle = the warp's staging-tile layout.
+  int use_tma_store;
+  CUtensorMap out_map;
   wfk_tap taps[WFK_MAX_TAPS];
 };
 
@@ -226,6 +230,14 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
   constexpr int kStAcc = 4 / kStPasses;            // coalesced accesses (8 rows x 64 B each) per pass
   // fp32 outputs (attention scores) of the plain-tap kernels: the same staging with 128-byte rows
   constexpr bool kCoalesceF32 = !HALO;
+  // The Cout = 128 layers at 384^2 are epilogue-bound (K = 9*128 gives the epilogue 0.28 tensor cycles per output) and
+  // `ncu` shows the epilogue warps waiting on shared-memory loads (the staged tile read back for the row-contiguous
+  // stores: short-scoreboard stalls, 14 % of their time, under the MMA's operand traffic). This kernel therefore hands
+  // the staged 32-pixel x 32-channel chunk to the TMA engine instead: 4 x STS, one fence, ONE cp.async.bulk.tensor by an
+  // elected lane -- no LDS, no STG, no per-lane output addressing, image-edge clipping by the tensor map.
+  // The 256-wide HALO kernel does the same with its 16-row staging tile (two 1 KB stores per chunk): its epilogue is not
+  // critical, but the LDS / STG / address work it no longer does is shared-memory bandwidth and power returned to the MMAs.
+  constexpr bool kTmaStore = HALO && !EPI;
   constexpr uint32_t kStageWarpBytes = HALO ? 2048u / kStPasses : 4096u;
   constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
   constexpr int kBBytes = kBRows * kBlockK * 2;
@@ -271,7 +283,9 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
   float* s_sh2 = s_sc2 + BN;
   // per-epilogue-warp staging tile (32 rows x 64 B, 16-byte units XOR-swizzled): turns the row-per-lane register
   // layout of a TMEM chunk into row-contiguous global accesses
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + BN * (EPI ? 3 : 1));
+  // (1 KB-aligned: the TMA store's 64-byte swizzle is a function of the shared-memory address bits 7-8)
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(s_bias + BN * (EPI ? 3 : 1)) + (kTmaStore ? 1023 : 0)) & ~uintptr_t(kTmaStore ? 1023 : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -838,7 +852,8 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       // K = 9*128 layers LSU-bound (measured: +23 % with the stores removed, +30 % on residual layers).
       int64_t cbase[MB][4];
       uint32_t cvalid = 0;
-      if constexpr (kCoalesce) {
+      const bool tma_store = kTmaStore && p.use_tma_store != 0;
+      if (kCoalesce && (!tma_store || has_res)) {   // per-lane output rows: the store path without TMA, the residual loads
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
           const int blk = static_cast<int>(cta_rank) * MB + mb;
@@ -973,6 +988,10 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
         if (has_res) {
           uint4 rrow[4];
           if constexpr (kCoalesce) {
+            if (tma_store) {   // the staging tile may still be the source of the previous chunk's TMA store
+              if (lane == 0) bulk_wait_group_read<0>();
+              __syncwarp();
+            }
             // coalesced pieces -> staging -> this lane's own row
 #pragma unroll
             for (int ps = 0; ps < kStPasses; ++ps) {
@@ -1054,6 +1073,26 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) h2[e] = A16<BF16>::pack(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
           }
+          if (tma_store) {
+#pragma unroll
+            for (int ps = 0; ps < kStPasses; ++ps) {
+              // the previous store must have finished READING the staging tile (issued one chunk / pass of work ago)
+              if (lane == 0) bulk_wait_group_read<0>();
+              __syncwarp();
+              if (kStPasses == 1 || own_pass == ps) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sts_v4(own_row + ((static_cast<uint32_t>(j) ^ own_x) << 4), up[j]);
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the TMA engine
+              __syncwarp();
+              if (lane == 0) {
+                const int blk = static_cast<int>(cta_rank) * MB + mb;
+                tma_store_4d(&p.out_map, stg, t.nt * BN + c0, (t.tx * kBlocksPerTile + blk) * 8,
+                             t.ty * 16 + quarter * 4 + ps * (kStRows / 8), t.frame);
+                bulk_commit_group();
+              }
+            }
+          } else
 #pragma unroll
           for (int ps = 0; ps < kStPasses; ++ps) {
             if (kStPasses == 1 || own_pass == ps) {
@@ -1136,6 +1175,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       if (do_stats && !reg_stats) fold_stats(t.frame, t.nt);
     }
     if (reg_stats && stats_frame >= 0) flush_reg_stats(stats_frame);
+    if (kTmaStore && lane == 0) bulk_wait_group<0>();   // this warp's output stores are complete before the CTA retires
   };
 
   if constexpr (kRegSplit) {
@@ -1206,7 +1246,8 @@ constexpr size_t conv_smem_bytes() {
   constexpr size_t ring = HALO ? Cfg::kStages * halo_stage + (Cfg::kMB == 1 ? (EPI ? 5 : 6) : 5) * b_bytes
                                : Cfg::kStages * (Cfg::kMB * kABytes + b_bytes);
   return 1024 /*align slack*/ + ring + (3 * Cfg::kStages + 2 * kHaloBStagesMax + 4) * 8 + 16 +
-         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + kEpiWarps * (HALO ? (BN == 256 ? 1024 : 2048) : 4096) + 64;
+         kEpiWarps * (BN / 2) * 4 + BN * 4 * (EPI ? 3 : 1) + kEpiWarps * (HALO ? (BN == 256 ? 1024 : 2048) : 4096) + 64 +
+         ((HALO && !EPI) ? 1024 : 0) /* 1 KB alignment of the TMA-store staging tiles */;
 }
 
 template <int BN, bool PAIR, bool HALO, bool EPI = false, bool BF16 = false>
@@ -1526,6 +1567,23 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   if (rc != WFK_OK) {
     delete plan;
     return rc;
+  }
+  p.use_tma_store = 0;
+  static const bool tma_store_enabled = !(std::getenv("WFK_TMA_STORE") && std::getenv("WFK_TMA_STORE")[0] == '0');   // A/B switch
+  if (tma_store_enabled && plan->halo && !plan->epi && d->out_h != nullptr && d->out_f == nullptr &&
+      d->n_total % plan->bn == 0 && d->num_phases == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_rows == d->tile_h &&
+      d->out_cols == d->tile_w && (reinterpret_cast<uintptr_t>(d->out_h) & 15) == 0) {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->n_total), static_cast<cuuint64_t>(d->out_cols),
+                          static_cast<cuuint64_t>(d->out_rows), static_cast<cuuint64_t>(d->n_frames)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(d->ldc) * 2, static_cast<cuuint64_t>(d->out_cols) * d->ldc * 2,
+                             static_cast<cuuint64_t>(d->out_rows) * d->out_cols * d->ldc * 2};
+    cuuint32_t box[4] = {32u, 8u, plan->bn == 128 ? 4u : 2u, 1u};   // one staging pass of an epilogue warp
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = wfk::g_encode_tiled(&p.out_map, d->operand_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                     4, d->out_h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) p.use_tma_store = 1;   // otherwise: the per-lane store path
   }
   const long total_tiles = static_cast<long>(p.num_phases) * p.n_frames * p.tiles_y * p.tiles_x * p.tiles_n;
   if (total_tiles > 0x3fffffffL) {
