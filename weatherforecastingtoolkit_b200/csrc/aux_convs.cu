@@ -24,52 +24,63 @@ __device__ __forceinline__ float aux_act(int kind, float x, float slope) {
 constexpr int kStemThreads = 256;
 constexpr int kStemPixPerBlock = 512;
 
-// One thread = 8 output channels of one output pixel per step; the 16 x cout weights live in shared memory,
-// the 16 inputs of a pixel are read once per thread (L1 broadcast among the threads sharing the pixel).
+// One thread = 8 output channels, looping over output pixels; its 16 x 8 weights live in REGISTERS (the first version
+// re-read them from shared memory for every pixel: 4 x LDS.128 per output value, shared-memory-bandwidth bound at 10x
+// the layer's HBM time -- 36 % of the discriminator's forward pass), the 16 inputs of a pixel are read once per thread
+// (L1 broadcast among the 8 threads sharing the pixel). 128 FMAs per 16 input loads and one 128-bit store.
 __global__ void __launch_bounds__(kStemThreads) conv4x4s2_c1in_kernel(
     const float* __restrict__ in, int h, int w, const float* __restrict__ wt, const float* __restrict__ bias, int cout,
     int act, float slope, __half* __restrict__ out, int act2, const float* __restrict__ scale2,
     const float* __restrict__ shift2, __half* __restrict__ out2) {
-  extern __shared__ float s_w[];  // [16][cout] + bias[cout] + scale2[cout] + shift2[cout]
-  float* s_b = s_w + 16 * cout;
-  float* s_s2 = s_b + cout;
-  float* s_h2 = s_s2 + cout;
-  for (int i = threadIdx.x; i < 16 * cout; i += blockDim.x) s_w[i] = wt[i];
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) {
-    s_b[i] = bias[i];
-    s_s2[i] = scale2 ? scale2[i] : 1.f;
-    s_h2[i] = shift2 ? shift2[i] : 0.f;
-  }
-  __syncthreads();
   const int n = blockIdx.y;
   const int oh = h >> 1, ow = w >> 1;
   const int octets = cout >> 3;
   const int oc = (threadIdx.x % octets) << 3;
   const int pl = threadIdx.x / octets;
   const int pstep = kStemThreads / octets;
+  float wr[16][8], br[8], s2[8], h2v[8];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + t * cout + oc));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + t * cout + oc + 4));
+    wr[t][0] = w0.x; wr[t][1] = w0.y; wr[t][2] = w0.z; wr[t][3] = w0.w;
+    wr[t][4] = w1.x; wr[t][5] = w1.y; wr[t][6] = w1.z; wr[t][7] = w1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = __ldg(bias + oc + j);
+    s2[j] = (out2 != nullptr && scale2) ? __ldg(scale2 + oc + j) : 1.f;
+    h2v[j] = (out2 != nullptr && shift2) ? __ldg(shift2 + oc + j) : 0.f;
+  }
   const float* inn = in + static_cast<int64_t>(n) * h * w;
   const int p_begin = blockIdx.x * kStemPixPerBlock;
   const int p_end = min(oh * ow, p_begin + kStemPixPerBlock);
-  for (int p = p_begin + pl; p < p_end; p += pstep) {
-    const int y = p / ow, x = p - y * ow;
+  // (y, x) of this thread's pixel are advanced incrementally and interior windows are read through one row pointer with
+  // immediate offsets: the first version spent ~480 integer instructions per pixel on a division, 16 bounds checks and
+  // 16 64-bit address computations next to its 128 FMAs (ncu: FFMA 21 % of 1.08 G warp instructions)
+  int p = p_begin + pl;
+  int y = p / ow, x = p - y * ow;
+#pragma unroll 1
+  for (; p < p_end; p += pstep) {
+    float z[16];
+    if (y > 0 && y < oh - 1 && x > 0 && x < ow - 1) {
+      const float* r0 = inn + (2 * y - 1) * w + (2 * x - 1);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) z[t] = __ldg(r0 + (t >> 2) * w + (t & 3));
+    } else {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int yy = 2 * y - 1 + (t >> 2), xx = 2 * x - 1 + (t & 3);
+        z[t] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(inn + yy * w + xx) : 0.f;
+      }
+    }
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = s_b[oc + j];
+    for (int j = 0; j < 8; ++j) acc[j] = br[j];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-      const int yy = 2 * y - 1 + (t >> 2), xx = 2 * x - 1 + (t & 3);
-      const float z = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(inn + yy * w + xx) : 0.f;
-      const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * cout + oc);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_w + t * cout + oc + 4);
-      acc[0] = fmaf(w0.x, z, acc[0]);
-      acc[1] = fmaf(w0.y, z, acc[1]);
-      acc[2] = fmaf(w0.z, z, acc[2]);
-      acc[3] = fmaf(w0.w, z, acc[3]);
-      acc[4] = fmaf(w1.x, z, acc[4]);
-      acc[5] = fmaf(w1.y, z, acc[5]);
-      acc[6] = fmaf(w1.z, z, acc[6]);
-      acc[7] = fmaf(w1.w, z, acc[7]);
-    }
+    for (int t = 0; t < 16; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wr[t][j], z[t], acc[j]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = aux_act(act, acc[j], slope);
     const int64_t o = (static_cast<int64_t>(n) * oh * ow + p) * cout + oc;
@@ -83,9 +94,14 @@ __global__ void __launch_bounds__(kStemThreads) conv4x4s2_c1in_kernel(
     if (out2 != nullptr) {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        h2[e] = __floats2half2_rn(aux_act(act2, fmaf(acc[2 * e], s_s2[oc + 2 * e], s_h2[oc + 2 * e]), slope),
-                                  aux_act(act2, fmaf(acc[2 * e + 1], s_s2[oc + 2 * e + 1], s_h2[oc + 2 * e + 1]), slope));
+        h2[e] = __floats2half2_rn(aux_act(act2, fmaf(acc[2 * e], s2[2 * e], h2v[2 * e]), slope),
+                                  aux_act(act2, fmaf(acc[2 * e + 1], s2[2 * e + 1], h2v[2 * e + 1]), slope));
       *reinterpret_cast<uint4*>(out2 + o) = u;
+    }
+    x += pstep;
+    while (x >= ow) {
+      x -= ow;
+      ++y;
     }
   }
 }
@@ -161,12 +177,8 @@ extern "C" int wfk_conv4x4s2_c1in(const float* in, int n, int h, int w, const fl
   WFK_REQUIRE(in && weight && bias && (out || out2), "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad shape %dx%dx%d", n, h, w);
   WFK_REQUIRE(cout % 8 == 0 && cout >= 8 && cout <= 2048 && wfk::kStemThreads % (cout / 8) == 0, "cout=%d unsupported", cout);
-  const size_t smem = static_cast<size_t>(19) * cout * sizeof(float);
-  static wfk::PerDeviceOnce attr_once;
-  if (wfk::PerDeviceOnce::Lock attr_lock{attr_once}; attr_lock.needed()) {
-    WFK_CUDA_CHECK(cudaFuncSetAttribute(wfk::conv4x4s2_c1in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_lock.finished();
-  }
+  const size_t smem = 0;   // weights, bias and the second affine map live in registers
+  WFK_REQUIRE((reinterpret_cast<uintptr_t>(weight) & 15) == 0, "weight must be 16-byte aligned");
   dim3 grid(((h / 2) * (w / 2) + wfk::kStemPixPerBlock - 1) / wfk::kStemPixPerBlock, n);
   wfk::conv4x4s2_c1in_kernel<<<grid, wfk::kStemThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       in, h, w, weight, bias, cout, act, act_slope, static_cast<__half*>(out), act2, scale2, shift2,
