@@ -406,3 +406,47 @@ def test_metric_accumulator_equals_concatenated_batch(lib):
     for k in b:
         both_nan = a[k] != a[k] and b[k] != b[k]
         assert both_nan or a[k] == b[k] or abs(a[k] - b[k]) <= 1e-7 * max(1.0, abs(b[k])), (k, a[k], b[k])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(lib):
+    """the library holds no 'current device'. Kernels that need > 48 KB of dynamic shared memory (the fused
+    skill scores, the conv-GEMM) run on cuda:1 while cuda:0 stays the caller's current device, from the main thread
+    and from a worker thread, and the caller's device is restored after every call."""
+    import threading
+
+    from oracle import metrics_oracle as MO
+    from weatherforecastingtoolkit_b200 import _cabi
+    from weatherforecastingtoolkit_b200 import metrics as M
+    from weatherforecastingtoolkit_b200.models.autoencoderkl import AutoencoderKL
+    from weatherforecastingtoolkit_b200.rollout import stage_vil
+    from weatherforecastingtoolkit_b200.synthetic import PATHB_AKL_CONFIG, make_akl_state_dict
+    torch.cuda.set_device(0)
+    p, t = metric_case_inputs("rand_2x10x64")
+    want = MO.integer_counts(p, t).tolist()
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        got = M.metric_partials(p.to(dev), t.to(dev))
+        assert got.counts.tolist() == want
+        assert torch.cuda.current_device() == 0
+    u8 = torch.randint(0, 256, (1, 32, 32, 25), dtype=torch.uint8)
+    assert torch.equal(stage_vil(u8.to("cuda:1")).cpu(), stage_vil(u8.to("cuda:0")).cpu())
+    sd = make_akl_state_dict(PATHB_AKL_CONFIG, 0)
+    outs = {}
+    for dev in ("cuda:0", "cuda:1"):
+        m = AutoencoderKL(**PATHB_AKL_CONFIG)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev)
+        x = (u8[..., :2].float() / 255).permute(0, 3, 1, 2).reshape(2, 1, 32, 32).to(dev)
+        outs[dev] = m.decode(m.encode(x).mode()).cpu()
+        assert torch.cuda.current_device() == 0
+    assert torch.equal(outs["cuda:0"], outs["cuda:1"])     # same kernels, same fixed-order reductions
+    res = {}
+
+    def worker():
+        res["counts"] = M.metric_partials(p.to("cuda:1"), t.to("cuda:1")).counts.tolist()
+
+    th = threading.Thread(target=worker)
+    th.start()
+    th.join()
+    assert res["counts"] == want
+    assert _cabi.load().wfk_nonfinite_status(1, 0) == 0

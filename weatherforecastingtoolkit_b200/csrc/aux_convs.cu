@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) logit_sums_kernel(const float* __restrict
 extern "C" int wfk_conv4x4s2_c1in(const float* in, int n, int h, int w, const float* weight, const float* bias,
                                   int cout, int act, float act_slope, void* out, int act2, const float* scale2,
                                   const float* shift2, void* out2, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, in);
   WFK_REQUIRE(in && weight && bias && (out || out2), "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad shape %dx%dx%d", n, h, w);
   WFK_REQUIRE(cout % 8 == 0 && cout >= 8 && cout <= 2048 && wfk::kStemThreads % (cout / 8) == 0, "cout=%d unsupported", cout);
@@ -188,7 +188,7 @@ extern "C" int wfk_conv4x4s2_c1in(const float* in, int n, int h, int w, const fl
 
 extern "C" int wfk_conv1x1_cout1(const void* in, int n, int h, int w, int cin, const float* weight, float bias, int pad,
                                  float* out, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, in);
   WFK_REQUIRE(in && weight && out, "null pointer");
   WFK_REQUIRE(n > 0 && h > 0 && w > 0 && cin > 0 && cin % 8 == 0 && pad >= 0, "bad shape");
   const int64_t total = static_cast<int64_t>(n) * (h + 2 * pad) * (w + 2 * pad);
@@ -201,7 +201,7 @@ extern "C" int wfk_conv1x1_cout1(const void* in, int n, int h, int w, int cin, c
 }
 
 extern "C" int wfk_logit_sums(const float* x, int64_t count, double* sums, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, x);
   WFK_REQUIRE(x && sums && count > 0, "bad argument");
   int64_t blocks = (count + 255) / 256;
   const int64_t cap = static_cast<int64_t>(wfk::num_sms()) * 8;

@@ -1613,9 +1613,7 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
 
 extern "C" int wfk_conv_plan_run(const wfk_conv_plan* plan, void* stream) {
   WFK_REQUIRE(plan != nullptr, "null plan");
-  WFK_ENTER_STREAM(stream);
-  WFK_REQUIRE(plan->device == wfk::t_device, "plan was created on device %d, stream belongs to device %d", plan->device,
-              wfk::t_device);
+  WFK_ENTER_DEVICE(plan->device);   // the device that holds the plan's operands; `stream` must belong to it
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (plan->epi) {

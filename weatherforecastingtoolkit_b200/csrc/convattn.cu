@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(kCaThreads, 1) convattn_kernel(const float* __
 // weatherforecastingtoolkit_b200/predictors.py::ConvAttnModel._weight_pointers).
 extern "C" int wfk_convattn_forward(const float* x, int n, int cin, int layers, int latent_dim, const float* const* weights,
                                     int num_weights, float* z, float* recon, double* huber_sums, int mode, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, (x != nullptr ? static_cast<const void*>(x) : static_cast<const void*>(z)));
   WFK_REQUIRE(weights && z, "null pointer");
   WFK_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (encode + decode), 1 (encode only) or 2 (decode only)");
   WFK_REQUIRE(mode == 2 || x != nullptr, "x is required unless decoding from z");

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kCmThreads, 1) convmodel_kernel(const float* _
 
 extern "C" int wfk_convmodel_forward(const float* x, int n, int cin, int latent_dim, const float* const* weights,
                                      float* z, float* recon, double* huber_sums, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, x);
   WFK_REQUIRE(x && weights && z && recon, "null pointer");
   WFK_REQUIRE(n > 0 && cin >= 1 && cin <= 8 && latent_dim >= 1 && latent_dim <= 4096, "bad shape");
   for (int i = 0; i < 34; ++i) WFK_REQUIRE(weights[i] != nullptr, "weights[%d] is NULL", i);

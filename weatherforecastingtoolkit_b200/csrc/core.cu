@@ -54,6 +54,16 @@ DeviceScope DeviceScope::from_stream(void* stream) {
   return DeviceScope(device);
 }
 
+DeviceScope DeviceScope::from_stream_or_pointer(void* stream, const void* device_ptr) {
+  // the pointer decides (capture-safe, unambiguous); the stream only when the call has no usable device pointer
+  cudaPointerAttributes attr;
+  if (device_ptr != nullptr && cudaPointerGetAttributes(&attr, device_ptr) == cudaSuccess &&
+      (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged))
+    return DeviceScope(attr.device);
+  cudaGetLastError();
+  return from_stream(stream);
+}
+
 DeviceScope DeviceScope::from_pointer(const void* device_ptr) {
   int device = -1;
   cudaPointerAttributes attr;

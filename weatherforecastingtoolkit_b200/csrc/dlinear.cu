@@ -125,7 +125,7 @@ extern "C" int wfk_dlinear(const float* x, int64_t x_batch_stride, const float* 
                            const float* w_trend, const float* b_trend, int nb, int seq_len, int pred_len, int channels,
                            int group, int kernel_size, int individual, int framed, float* pred, float* tgt,
                            double* loss_sums, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, x);
   WFK_REQUIRE(x && w_seasonal && b_seasonal && w_trend && b_trend && pred, "null pointer");
   WFK_REQUIRE(nb > 0 && seq_len > 0 && pred_len > 0 && channels > 0, "empty problem");
   WFK_REQUIRE(kernel_size >= 1 && (kernel_size & 1), "kernel_size=%d must be odd (the reference pads (k-1)/2 per side)",

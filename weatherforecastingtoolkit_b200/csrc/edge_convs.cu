@@ -210,7 +210,7 @@ int wfk_launch_c1in(const float* in, int n, int h, int w, const float* weight, c
 extern "C" int wfk_conv3x3_small_cin(const float* in, int n, int cin, int h, int w, const float* pre_w,
                                      const float* pre_b, const float* weight, const float* bias, int cout, void* out,
                                      double* stats, int cpg, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, in);
   WFK_REQUIRE(in && weight && bias && out, "null pointer");
   WFK_REQUIRE(cin >= 1 && cin <= wfk::kMaxCin, "cin=%d unsupported (1..%d)", cin, wfk::kMaxCin);
   WFK_REQUIRE(cout % 8 == 0 && cout >= 8 && cout <= 2048 && 256 % (cout / 8) == 0, "cout=%d unsupported", cout);
@@ -236,7 +236,7 @@ extern "C" int wfk_conv3x3_small_cout(const void* in, int n, int h, int w, int c
 extern "C" int wfk_conv3x3_small_cout_act(const void* in, int n, int h, int w, int cin, const void* weight_h,
                                           const float* bias, int cout, const float* post_w, const float* post_b,
                                           int act, float* out, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, in);
   WFK_REQUIRE(act == WFK_ACT_NONE || act == WFK_ACT_SIGMOID, "act must be none or sigmoid");
   WFK_REQUIRE(in && weight_h && bias && out, "null pointer");
   WFK_REQUIRE(cin % 8 == 0 && cin > 0, "cin must be a multiple of 8");

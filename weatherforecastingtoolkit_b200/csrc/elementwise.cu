@@ -247,7 +247,7 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, int64_t n, __hal
 extern "C" int wfk_groupnorm_apply(const void* x, const double* stats, const float* gamma, const float* beta, int n,
                                    int hw, int c, int groups, float eps, int apply_silu, void* out, int bf16,
                                    void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, x);
   WFK_REQUIRE(x && stats && gamma && beta && out, "null pointer");
   WFK_REQUIRE(n > 0 && hw > 0 && c > 0 && groups > 0, "empty problem");
   WFK_REQUIRE(c % 8 == 0 && c % groups == 0 && c <= 2048 && 256 % (c / 8) == 0 && groups <= 256,
@@ -268,7 +268,7 @@ extern "C" int wfk_groupnorm_apply(const void* x, const double* stats, const flo
 
 extern "C" int wfk_gn_table(const double* stats, const float* gamma, const float* beta, int n, int hw, int c,
                             int groups, float eps, void* table, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, stats);
   WFK_REQUIRE(stats && gamma && beta && table, "null pointer");
   WFK_REQUIRE(n > 0 && hw > 0 && c > 0 && groups > 0 && c % groups == 0, "bad shape");
   cudaLaunchConfig_t cfg{};
@@ -288,7 +288,7 @@ extern "C" int wfk_gn_table(const double* stats, const float* gamma, const float
 
 extern "C" int wfk_softmax_rows(const float* scores, int64_t rows, int cols, float scale, void* probs, int bf16,
                                 void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, scores);
   WFK_REQUIRE(scores && probs, "null pointer");
   WFK_REQUIRE(rows > 0 && rows < (1ll << 31) && cols > 0 && cols <= 11264, "unsupported softmax shape");
   if (cols % 4 == 0 && cols <= 4096) {
@@ -311,7 +311,7 @@ extern "C" int wfk_softmax_rows(const float* scores, int64_t rows, int cols, flo
 
 extern "C" int wfk_gaussian_posterior(const float* moments, int n, int lc, int hw, float* logvar, float* std, float* var,
                                       const float* noise, float* sample, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, moments);
   WFK_REQUIRE(moments && n > 0 && lc > 0 && hw > 0, "bad argument");
   WFK_REQUIRE((sample == nullptr) == (noise == nullptr), "noise and sample must both be given or both NULL");
   const int64_t total = static_cast<int64_t>(n) * lc * hw;
@@ -321,7 +321,7 @@ extern "C" int wfk_gaussian_posterior(const float* moments, int n, int lc, int h
 }
 
 extern "C" int wfk_nhwc_to_nchw_f32(const float* in, int n, int hw, int c, float* out, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, in);
   WFK_REQUIRE(in && out && n > 0 && hw > 0 && c > 0, "bad argument");
   const int64_t total = static_cast<int64_t>(n) * hw * c;
   wfk::nhwc_to_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -330,7 +330,7 @@ extern "C" int wfk_nhwc_to_nchw_f32(const float* in, int n, int hw, int c, float
 }
 
 extern "C" int wfk_f32_to_f16(const float* in, int64_t n, void* out, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, in);
   WFK_REQUIRE(in && out && n > 0, "bad argument");
   const int64_t blocks = (n + 255) / 256;
   wfk::f32_to_f16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(

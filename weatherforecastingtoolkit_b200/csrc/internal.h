@@ -59,6 +59,7 @@ struct DeviceScope {
   void enter(int device);
   explicit DeviceScope(int device) { enter(device); }
   static DeviceScope from_stream(void* stream);
+  static DeviceScope from_stream_or_pointer(void* stream, const void* device_ptr);
   static DeviceScope from_pointer(const void* device_ptr);
   DeviceScope(const DeviceScope&) = delete;
   DeviceScope(DeviceScope&& o) noexcept : status(o.status), dev(o.dev), prev(o.prev), saved(o.saved), switched(o.switched) {
@@ -69,6 +70,14 @@ struct DeviceScope {
 };
 #define WFK_ENTER_STREAM(stream)                                            \
   ::wfk::DeviceScope _wfk_scope = ::wfk::DeviceScope::from_stream(stream);  \
+  if (_wfk_scope.status != WFK_OK) return _wfk_scope.status
+// The usual form: the device of `devptr` (a device pointer argument of the call). A stream handle alone cannot tell:
+// the legacy default stream is handle 0 on EVERY device, which is what PyTorch hands over for a device's default stream.
+#define WFK_ENTER(stream, devptr)                                                            \
+  ::wfk::DeviceScope _wfk_scope = ::wfk::DeviceScope::from_stream_or_pointer(stream, devptr); \
+  if (_wfk_scope.status != WFK_OK) return _wfk_scope.status
+#define WFK_ENTER_DEVICE(dev)             \
+  ::wfk::DeviceScope _wfk_scope(dev);     \
   if (_wfk_scope.status != WFK_OK) return _wfk_scope.status
 #define WFK_ENTER_PTR(ptr)                                                  \
   ::wfk::DeviceScope _wfk_scope = ::wfk::DeviceScope::from_pointer(ptr);    \

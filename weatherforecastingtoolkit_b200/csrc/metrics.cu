@@ -604,7 +604,7 @@ extern "C" size_t wfk_metrics_workspace_bytes(int frames, int h, int w) {
 extern "C" int wfk_metrics(const float* pred, const float* tgt, int frames, int h, int w, const float* thresholds,
                            int n_thresholds, int clamp01, wfk_metric_partials* out, void* workspace,
                            size_t workspace_bytes, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, pred);
   WFK_REQUIRE(pred && tgt && out && workspace && thresholds, "null pointer");
   WFK_REQUIRE(frames > 0 && frames <= 65535, "frames=%d unsupported (1..65535 per call)", frames);
   WFK_REQUIRE(h >= 11 && w >= 11, "SSIM needs h, w >= 11 (got %dx%d)", h, w);

@@ -138,7 +138,7 @@ static unsigned gen_grid(int64_t items) {
 extern "C" int wfk_pooled_counts(const float* pred, const float* tgt, int frames, int h, int w, int pool_kind, int scale,
                                  const float* thresholds, int n_thresholds, int clamp01, int64_t* counts, double* sums,
                                  void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, pred);
   WFK_REQUIRE(pred && tgt && counts && sums, "null pointer");
   WFK_REQUIRE(frames > 0 && h > 0 && w > 0, "empty problem");
   WFK_REQUIRE(pool_kind >= 0 && pool_kind <= 2 && scale >= 1 && (pool_kind != 0 || scale == 1), "bad pooling (kind %d, scale %d)",
@@ -156,7 +156,7 @@ extern "C" int wfk_pooled_counts(const float* pred, const float* tgt, int frames
 
 extern "C" int wfk_crps_ensemble(const float* pred, const float* tgt, int b, int n, int tc, int h, int w, int pool_kind,
                                  int scale, int clamp01, double* sums, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, pred);
   WFK_REQUIRE(pred && tgt && sums, "null pointer");
   WFK_REQUIRE(b > 0 && n > 0 && tc > 0 && h > 0 && w > 0, "empty problem");
   WFK_REQUIRE(pool_kind >= 0 && pool_kind <= 2 && scale >= 1 && (pool_kind != 0 || scale == 1) && scale <= h && scale <= w,
@@ -168,7 +168,7 @@ extern "C" int wfk_crps_ensemble(const float* pred, const float* tgt, int b, int
 }
 
 extern "C" int wfk_ensemble_mean(const float* pred, int b, int n, int64_t inner, int clamp01, float* out, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, pred);
   WFK_REQUIRE(pred && out && b > 0 && n > 0 && inner > 0, "bad argument");
   wfk::ensemble_mean_kernel<<<wfk::gen_grid(static_cast<int64_t>(b) * inner), wfk::kGenThreads, 0,
                               static_cast<cudaStream_t>(stream)>>>(pred, b, n, inner, clamp01 ? 1 : 0, out);

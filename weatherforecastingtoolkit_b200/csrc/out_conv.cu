@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kOutThreads) gn_silu_conv3x3_c1_kernel(
 extern "C" int wfk_gn_silu_conv3x3_c1(const void* x, const double* stats, const float* gamma, const float* beta, int n,
                                       int h, int w, int c, int groups, float eps, const float* weight, float bias,
                                       float* out, int bf16, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, x);
   WFK_REQUIRE(x && stats && gamma && beta && weight && out, "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0, "bad shape");
   WFK_REQUIRE(c % 8 == 0 && c > 0 && c <= 1024 && c % groups == 0 && groups <= 256, "unsupported c=%d groups=%d", c, groups);

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kPredTcThreads, 3) predict_linear_tc_kernel(
 
 extern "C" int wfk_predict_linear(const float* lat, const float* weight, const float* bias, int b, int t_in, int t_out,
                                   int c, int hw, float* pred, float* tgt, double* loss_sums, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, lat);
   WFK_REQUIRE(lat && weight && bias && pred, "null pointer");
   WFK_REQUIRE(b > 0 && t_in > 0 && t_out > 0 && c > 0 && hw > 0, "empty problem");
   const int K = t_in * c, N = t_out * c;

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) render_panels_kernel(const float* __restr
 extern "C" int wfk_render_panels(const float* pred, const float* tgt, int64_t count, const uint8_t* lut_vil_rgba,
                                  const uint8_t* lut_diff_rgba, uint8_t* tgt_u8, uint8_t* pred_u8, uint8_t* diff_u8,
                                  uint8_t* tgt_rgba, uint8_t* pred_rgba, uint8_t* diff_rgba, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, pred);
   WFK_REQUIRE(pred && tgt && lut_vil_rgba && lut_diff_rgba, "null pointer");
   WFK_REQUIRE(count > 0, "empty problem");
   auto aligned = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) stage_vil_seq_kernel(const uint8_t* __res
 
 extern "C" int wfk_stage_vil_u8(const uint8_t* nhwt, int n, int h, int w, int t, void* out_ntchw, int out_dtype,
                                 void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, nhwt);
   WFK_REQUIRE(nhwt && out_ntchw, "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && t > 0 && t <= 64, "unsupported shape n=%d h=%d w=%d t=%d", n, h, w, t);
   WFK_REQUIRE(out_dtype == 0 || out_dtype == 1, "out_dtype must be 0 (f32) or 1 (f16)");
@@ -148,7 +148,7 @@ extern "C" int wfk_stage_vil_u8(const uint8_t* nhwt, int n, int h, int w, int t,
 extern "C" int wfk_stage_vil_windows_ex(const uint8_t* events, int num_events, int h, int w, int t_raw, const int32_t* windows,
                                         int n, int t, float scale, float offset, void* out_ntchw, int out_dtype,
                                         void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, events);
   WFK_REQUIRE(events && windows && out_ntchw, "null pointer");
   WFK_REQUIRE(num_events > 0 && n > 0 && n <= 65535 && h > 0 && w > 0, "unsupported shape");
   WFK_REQUIRE(t > 0 && t <= t_raw && t_raw <= 64, "need 0 < t (%d) <= t_raw (%d) <= 64", t, t_raw);

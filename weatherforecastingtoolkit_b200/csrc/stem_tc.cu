@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_s
 
 extern "C" int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w, int ones_plane, const void* weight_h,
                                    const float* bias, int cout, void* out, double* stats, int cpg, int bf16, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, in);
   WFK_REQUIRE(in && weight_h && bias && out, "null pointer");
   WFK_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && cin >= 1, "bad shape");
   const int K = (cin + (ones_plane ? 1 : 0)) * 9;

@@ -199,7 +199,7 @@ inline unsigned grid_for(int64_t total, int per_block) {
 }  // namespace wfk
 
 extern "C" int wfk_patchify16(const float* img, int n, int h, int w, void* rows, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, img);
   WFK_REQUIRE(img && rows && n > 0 && h > 0 && w > 0 && h % 16 == 0 && w % 16 == 0, "bad argument (h, w multiples of 16)");
   const int64_t total = static_cast<int64_t>(n) * h * w;
   wfk::patchify16_kernel<<<wfk::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -208,7 +208,7 @@ extern "C" int wfk_patchify16(const float* img, int n, int h, int w, void* rows,
 }
 
 extern "C" int wfk_unpatchify16(const float* rows, int n, int h, int w, float* img, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, rows);
   WFK_REQUIRE(img && rows && n > 0 && h > 0 && w > 0 && h % 16 == 0 && w % 16 == 0, "bad argument (h, w multiples of 16)");
   const int64_t total = static_cast<int64_t>(n) * h * w;
   wfk::unpatchify16_kernel<<<wfk::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, n, h, w, img);
@@ -216,7 +216,7 @@ extern "C" int wfk_unpatchify16(const float* rows, int n, int h, int w, float* i
 }
 
 extern "C" int wfk_mha_small(const void* qkv, int n, int tokens, int d_model, int heads, void* out, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, qkv);
   WFK_REQUIRE(qkv && out && n > 0 && n <= 65535, "bad argument");
   WFK_REQUIRE(tokens >= 1 && tokens <= wfk::kMhaT, "tokens=%d unsupported (1..%d)", tokens, wfk::kMhaT);
   WFK_REQUIRE(heads >= 1 && d_model == heads * wfk::kMhaD, "d_model=%d must be heads (%d) x 64", d_model, heads);
@@ -233,7 +233,7 @@ extern "C" int wfk_mha_small(const void* qkv, int n, int tokens, int d_model, in
 
 extern "C" int wfk_cross_encode_attn(const float* q_scaled, const void* kv, int n, int tokens, int d_latent, int heads,
                                      void* out, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, kv);
   WFK_REQUIRE(q_scaled && kv && out && n > 0 && n <= 65535, "bad argument");
   WFK_REQUIRE(tokens >= 1 && tokens <= 128 && heads >= 1 && d_latent % heads == 0, "bad shape");
   wfk::cross_encode_attn_kernel<<<dim3(heads, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -243,7 +243,7 @@ extern "C" int wfk_cross_encode_attn(const float* q_scaled, const void* kv, int 
 
 extern "C" int wfk_layernorm_rows(const float* x, int64_t rows, int d, const float* gamma, const float* beta, float eps,
                                   void* out_h, float* out_f, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, x);
   WFK_REQUIRE(x && gamma && beta && (out_h || out_f) && rows > 0 && d > 0, "bad argument");
   const int64_t blocks = (rows + 7) / 8;
   wfk::layernorm_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -252,7 +252,7 @@ extern "C" int wfk_layernorm_rows(const float* x, int64_t rows, int d, const flo
 }
 
 extern "C" int wfk_bcast_add_rows(const float* vec, const float* pos, int n, int tokens, int d, void* out, void* stream) {
-  WFK_ENTER_STREAM(stream);
+  WFK_ENTER(stream, vec);
   WFK_REQUIRE(vec && pos && out && n > 0 && tokens > 0 && d > 0, "bad argument");
   const int64_t total = static_cast<int64_t>(n) * tokens * d;
   wfk::bcast_add_rows_kernel<<<wfk::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
