@@ -64,13 +64,22 @@ class _DLinearBase(nn.Module):
         self._packed = None
 
     # ------------------------------------------------------------------ weights in kernel layout
+    def repack(self) -> None:
+        """Drop the packed weights: call after writing parameters through ``.data`` (no version bump) or, for the
+        ``individual`` form, to skip the per-call version walk by freezing the pack (``freeze_pack = True``)."""
+        self._packed = None
+
+    freeze_pack = False   # True: trust the cached pack without re-checking ~37k parameter versions per call (individual)
+
     def _pack(self, device) -> Tuple[torch.Tensor, ...]:
         """fp32 device copies: shared [P, L] / [P]; individual: the ModuleList stacked to [channels, P, L] /
-        [channels, P]. Cached until a parameter changes (version counters)."""
+        [channels, P]. Cached until a parameter changes: keyed on (data_ptr, version) of EVERY tensor (a sum of versions
+        can collide, and replacing a Parameter changes its data_ptr); ``.data`` writes need an explicit ``repack()``."""
+        if self.freeze_pack and self._packed is not None and self._packed[0][0] == str(device):
+            return self._packed[1]
         mods = (list(self.Linear_Seasonal) + list(self.Linear_Trend)) if self.individual else \
             [self.Linear_Seasonal, self.Linear_Trend]
-        key = (str(device), sum(p._version for m in mods for p in (m.weight, m.bias)),
-               tuple(p.data_ptr() for m in (mods[0], mods[-1]) for p in (m.weight, m.bias)))
+        key = (str(device), tuple((p.data_ptr(), p._version) for m in mods for p in (m.weight, m.bias)))
         if self._packed is not None and self._packed[0] == key:
             return self._packed[1]
         with torch.no_grad():
@@ -205,7 +214,7 @@ class ConvModel(nn.Module):
 
     def _pack(self, device):
         mods = self._modules_in_kernel_order()
-        key = (str(device), sum(p._version for p in self.parameters()))
+        key = (str(device), tuple((p.data_ptr(), p._version) for p in self.parameters()))
         if self._packed is not None and self._packed[0] == key:
             return self._packed[1]
         import ctypes as C
@@ -316,7 +325,7 @@ class ConvAttnModel(nn.Module):
 
     def _pack(self, device):
         params = self._weight_pointers()
-        key = (str(device), sum(p._version for p, _ in params), tuple(p.data_ptr() for p, _ in params))
+        key = (str(device), tuple((p.data_ptr(), p._version) for p, _ in params))
         if self._packed is not None and self._packed[0] == key:
             return self._packed[1]
         import ctypes as C
