@@ -191,6 +191,26 @@ def predictor_rollout(v, weight, bias, in_frames: int = 13):
     return pred + inp_t, tgt + inp_t, loss
 
 
+def predictor_autoregressive(inp, weight, bias, blocks: int):
+    """The same ``Linear(13*C -> 12*C)`` predictor stepped autoregressively (north_star: "a linear latent predictor
+    stepped autoregressively"; the reference experiment itself applies it once, ``train.py:100-113``): each block of 12
+    predicted frames is appended and the next block is predicted from the LAST 13 frames of the sequence so far, with
+    the residual framing of ``train.py:104-112`` re-anchored on the newest frame. inp [B, 13, C, h, w] ->
+    [B, 12 * blocks, C, h, w]."""
+    b, t_in, c, h, w = inp.shape
+    t_out = weight.shape[0] // c
+    seq = inp
+    outs = []
+    for _ in range(blocks):
+        win = seq[:, -t_in:]
+        last = win[:, -1].unsqueeze(1)
+        x = (win - last).permute(0, 3, 4, 1, 2).reshape(b, h, w, t_in * c)
+        pred = F.linear(x, weight, bias).permute(0, 3, 1, 2).reshape(b, t_out, c, h, w) + last
+        outs.append(pred)
+        seq = torch.cat([seq, pred], dim=1)
+    return torch.cat(outs, dim=1)
+
+
 def validation_step(batch_nhwt, sd: SD, cfg: dict, weight, bias, in_frames: int = 13, **kw):
     """``Model.validation_step`` (``train.py:100-120``) up to the tensors handed to
     ``log_metrics``: returns (decoded_pred, decoded_tgt, val_loss)."""

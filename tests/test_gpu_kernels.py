@@ -66,6 +66,26 @@ def test_predictor_vs_oracle(lib, b, hw):
     assert loss.item() == pytest.approx(loss_o.item(), rel=1e-5)
 
 
+def test_predictor_autoregressive_vs_oracle(lib):
+    """north_star: the linear latent predictor stepped autoregressively (blocks of 12 frames from the last 13)."""
+    from oracle import akl_oracle as O
+    from weatherforecastingtoolkit_b200.rollout import LatentLinearPredictor
+    from weatherforecastingtoolkit_b200.synthetic import make_predictor_params
+    w, bias = make_predictor_params(seed=5)
+    torch.manual_seed(11)
+    inp = torch.randn(2, 13, 4, 12, 12)
+    want = O.predictor_autoregressive(inp, w, bias, blocks=3)
+    p = LatentLinearPredictor()
+    p.weight.data.copy_(w)
+    p.bias.data.copy_(bias)
+    got = p.rollout_autoregressive(inp.to(DEV), blocks=3)
+    assert got.shape == (2, 36, 4, 12, 12)
+    assert torch.allclose(got.cpu(), want, atol=2e-5, rtol=1e-4)
+    # the first block is the one-shot rollout of the reference step
+    one, _, _ = p.rollout(torch.cat([inp, torch.zeros(2, 12, 4, 12, 12)], 1).to(DEV))
+    assert torch.equal(one, got[:, :12])
+
+
 # ------------------------------------------------------------------ metrics
 @pytest.mark.parametrize("name", METRIC_CASES)
 def test_metrics_vs_golden(lib, golden_metrics, name):

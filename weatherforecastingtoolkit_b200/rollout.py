@@ -117,6 +117,36 @@ class LatentLinearPredictor(nn.Linear):
         return pred, tgt, (loss[0] / loss[1]).to(torch.float32)
 
 
+    @torch.no_grad()
+    def rollout_autoregressive(self, inp: torch.Tensor, blocks: int = 2) -> torch.Tensor:
+        """The predictor stepped autoregressively (north_star; the reference experiment applies it once): every call of
+        the fused kernel yields ``pred_frames`` frames from the last ``input_frames`` frames of the sequence so far,
+        re-anchoring the residual framing of train.py:104-112 on the newest frame. inp [B, input_frames, C, h, w] ->
+        [B, pred_frames * blocks, C, h, w]. One kernel launch per block; the window lives in one reused device buffer."""
+        lib = _lib_for(inp)
+        b, t, c, h, w = inp.shape
+        if t != self.input_frames or c != self.latent_channels:
+            raise ValueError(f"expected [B, {self.input_frames}, {self.latent_channels}, h, w] input latents")
+        if blocks < 1:
+            raise ValueError("blocks must be >= 1")
+        ti, to = self.input_frames, self.pred_frames
+        wt = self.weight.detach().to(device=inp.device, dtype=torch.float32).contiguous()
+        bs = self.bias.detach().to(device=inp.device, dtype=torch.float32).contiguous()
+        win = torch.zeros((b, ti + to, c, h, w), dtype=torch.float32, device=inp.device)   # kernel layout: inputs | targets
+        win[:, :ti] = inp.detach().to(torch.float32)
+        out = torch.empty((b, to * blocks, c, h, w), dtype=torch.float32, device=inp.device)
+        pred = torch.empty((b, to, c, h, w), dtype=torch.float32, device=inp.device)
+        stream = torch.cuda.current_stream(inp.device).cuda_stream
+        for k in range(blocks):
+            _cabi.check(lib.wfk_predict_linear(win.data_ptr(), wt.data_ptr(), bs.data_ptr(), b, ti, to, c, h * w,
+                                               pred.data_ptr(), None, None, stream), "wfk_predict_linear")
+            out[:, k * to:(k + 1) * to] = pred
+            if k + 1 < blocks:      # next window = last `ti` frames of (window inputs, prediction)
+                seq = torch.cat([win[:, :ti], pred], dim=1)
+                win[:, :ti] = seq[:, -ti:]
+        return out
+
+
 class Autoencoder(nn.Module):
     """The train script's frozen-AE wrapper (train.py:21-56): ``encode([B,T,C,H,W]) -> [B,T,LC,h,w]``,
     ``decode([B,T,LC,h,w]) -> [B,T,1,H,W]``. The reference loops over T with batch B; frames are
