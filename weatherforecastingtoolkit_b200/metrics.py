@@ -122,11 +122,12 @@ def metric_partials_device(pred: torch.Tensor, target: torch.Tensor, thresholds:
         nf = min(frames - done, 65535)
         ws_bytes = lib.wfk_metrics_workspace_bytes(nf, h, w)
         key = (str(dev), ws_bytes)
-        ws = _workspaces.get(key)
+        ws = _workspaces.pop(key, None)
         if ws is None:
+            while len(_workspaces) >= 4:          # a few shapes per process (LRU); single-stream use per device
+                _workspaces.pop(next(iter(_workspaces)))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            _workspaces.clear()
-            _workspaces[key] = ws
+        _workspaces[key] = ws
         part = out if done == 0 else torch.empty_like(out)
         with _engine.timed_pass("metrics", 8.0 * nf * h * w):   # algorithmic traffic: pred + target read once
             _cabi.check(lib.wfk_metrics(p[done:].data_ptr(), t[done:].data_ptr(), nf, h, w, thr, len(thresholds),
