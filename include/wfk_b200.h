@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WFK_ABI_VERSION 2
+#define WFK_ABI_VERSION 3
 
 enum wfk_status {
   WFK_OK = 0,
@@ -211,7 +211,19 @@ enum wfk_act {
   WFK_ACT_LEAKY_RELU = 1, /* slope = act_slope (nn.LeakyReLU(0.2), losses/model.py:121)          */
   WFK_ACT_GELU = 2,       /* exact erf form (nn.GELU(), ae_64x8x8_lin.py:15, ae_vit.py:112)       */
   WFK_ACT_SIGMOID = 3,    /* nn.Sigmoid (ae_64x8x8_lin.py:85)                                      */
-  WFK_ACT_SILU = 4
+  WFK_ACT_SILU = 4,
+  /* Row-wise softmax split over three GEMM launches (attention.py:163-176: baddbmm -> softmax(fp32) -> bmm) so that
+   * the fp32 score matrix never exists in memory. Plain one-tap GEMM descriptors only (`act` field, fp16 operands):
+   *   ROW_MAX : no tensor output; row_out[row][slot] = max over the slot's columns of D          (pass 1: Q K^T)
+   *   ROW_EXP : m = max_slot row_in[row][slot]; out_h = exp2((D - m) * row_scale);
+   *             row_out[row][slot] = sum over the slot's columns of that value (fp32)             (pass 2: Q K^T again)
+   *   ROW_NORM: out = D / (sum_slot row_in[row][slot]) + shift2[c]                                (pass 3: P V)
+   * row = frame * out_rows * out_cols + pixel; every (row, slot) is written by exactly one thread, in a fixed
+   * order, so the results are deterministic. row_ld = number of slots = 2 * ceil(n_total / 256) of the GEMM that WRITES
+   * them (128 instead of 256 when n_total < 256 and not a multiple of 256); ROW_NORM reads its producer's row_ld. */
+  WFK_ACT_ROW_MAX = 5,
+  WFK_ACT_ROW_EXP = 6,
+  WFK_ACT_ROW_NORM = 7
 };
 
 typedef struct wfk_conv_desc {
@@ -256,6 +268,11 @@ typedef struct wfk_conv_desc {
   void* out2_h;          /* fp16 or NULL                                                        */
   const float* scale2;   /* [n_total] or NULL (= 1)                                             */
   const float* shift2;   /* [n_total] or NULL (= 0)                                             */
+  /* WFK_ACT_ROW_* only (see wfk_act): per-row partials, [rows][row_ld] fp32 */
+  const float* row_in;
+  float* row_out;
+  int32_t row_ld;
+  float row_scale;       /* ROW_EXP: log2(e) * softmax scale                                    */
 } wfk_conv_desc;
 
 typedef struct wfk_conv_plan wfk_conv_plan;

@@ -34,7 +34,7 @@ def test_binding_covers_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.wfk_abi_version() == 2
+    assert lib.wfk_abi_version() == 3
     assert lib.wfk_strerror(0) == b"ok"
     assert b"invalid" in lib.wfk_strerror(-1)
 

@@ -139,6 +139,63 @@ def test_groupnorm_silu(engine):
         assert rel_l2(out.float(), ref) < 5e-4
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 12, 20), (3, 20, 26), (1, 48, 48)])
+@pytest.mark.parametrize("qscale", [1.0, 16.0])
+@pytest.mark.parametrize("fused", [False, True])
+def test_attention_block_vs_fp32(engine, akl_weights, n, h, w, qscale, fused):
+    """The mid-block attention alone (GroupNorm -> q, k, v -> softmax(q k^T / sqrt(c)) v -> proj + residual,
+    /root/reference/pipeline/models/autoencoderkl/attention.py:136-189) against the same arithmetic in fp32, for the
+    default chain (fp32 scores -> wfk_softmax_rows -> P V) and the opt-in one without a score matrix
+    (WFK_ATTN_FUSED=1: row max, exp + row sums, P V / sum as GEMM epilogues). Token counts with ragged M and N tiles
+    (240, 520) and the production 2304; `qscale` multiplies the query projection so that the softmax rows go from nearly flat to
+    nearly one-hot (max-subtraction and the 16-bit probabilities both matter there)."""
+    from weatherforecastingtoolkit_b200 import _cabi
+    from weatherforecastingtoolkit_b200.engine import _Act
+    cfg, sd = akl_weights
+    p = "encoder.mid_block.attentions.0"
+    c = sd[p + ".query.weight"].shape[0]
+    torch.manual_seed(n * 100 + h)
+    x = torch.randn(n, h, w, c, device=DEV).half()
+    t = engine.w.t
+    saved = {k: t[p + k].clone() for k in (".qk.w", ".qk.bias")}
+    was_fused = engine.attn_fused
+    try:
+        engine.attn_fused = fused
+        t[p + ".qk.w"][0, :c] *= qscale
+        t[p + ".qk.bias"][:c] *= qscale
+        hs = _Harness(engine, n)
+        st = hs._new_stats()
+        out = hs.attention(_Act(x, st), p)
+        names = [what for _, _, what, *_ in hs.ops]
+        assert any("softmax" in k for k in names) != fused and any("scores(max)" in k for k in names) == fused
+        hs.stats_arena.zero_()
+        st.copy_(_ref_stats(x.float(), engine.groups))
+        stream = torch.cuda.current_stream().cuda_stream
+        for fn, args, what, *_ in hs.ops:
+            _cabi.check(fn(*args, stream), what)
+        torch.cuda.synchronize()
+    finally:
+        engine.attn_fused = was_fused
+        for k, v in saved.items():
+            t[p + k].copy_(v)
+    g = lambda k: sd[p + k].to(DEV).float()
+    xr = x.float().permute(0, 3, 1, 2)
+    hn = F.group_norm(xr, engine.groups, g(".group_norm.weight"), g(".group_norm.bias"), 1e-6)
+    hn = hn.reshape(n, c, h * w).transpose(1, 2)
+    q = (hn @ g(".query.weight").T + g(".query.bias")) * qscale
+    k = hn @ g(".key.weight").T + g(".key.bias")
+    v = hn @ g(".value.weight").T + g(".value.bias")
+    pr = torch.softmax(torch.bmm(q, k.transpose(1, 2)) / math.sqrt(c), dim=-1)
+    if qscale > 1:
+        assert pr.max(dim=-1).values.median().item() > 4.0 / (h * w)   # the rows are not flat any more
+    o = torch.bmm(pr, v) @ g(".proj_attn.weight").T + g(".proj_attn.bias")
+    ref = (o.transpose(1, 2).reshape(n, c, h, w) + xr).permute(0, 2, 3, 1)
+    assert rel_l2(out.t.float(), ref) < 1.5e-3
+    # the attention branch on its own (the residual dominates the sum; the 16-bit store of the sum bounds this one)
+    assert rel_l2(out.t.float() - x.float(), ref - x.float()) < 2e-2
+    assert rel_l2(out.stats, _ref_stats(ref, engine.groups)) < 2e-3
+
+
 @pytest.mark.parametrize("tag,hw,seed", [("akl64", 64, 11), ("akl384", 384, 12)])
 def test_akl_vs_reference_golden(model, golden_akl, tag, hw, seed):
     """encode -> moments and decode(golden z) against outputs of the UNMODIFIED reference."""

@@ -59,10 +59,11 @@ class ConvDesc(C.Structure):
         ("gn_groups", C.c_int32),
         ("act", C.c_int32), ("act2", C.c_int32), ("act_slope", C.c_float),
         ("out2_h", C.c_void_p), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
+        ("row_in", C.c_void_p), ("row_out", C.c_void_p), ("row_ld", C.c_int32), ("row_scale", C.c_float),
     ]
 
 
-ACT_NONE, ACT_LEAKY_RELU, ACT_GELU, ACT_SIGMOID, ACT_SILU = range(5)
+ACT_NONE, ACT_LEAKY_RELU, ACT_GELU, ACT_SIGMOID, ACT_SILU, ACT_ROW_MAX, ACT_ROW_EXP, ACT_ROW_NORM = range(8)
 
 
 _PROTOTYPES = {

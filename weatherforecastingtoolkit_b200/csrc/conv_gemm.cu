@@ -107,6 +107,11 @@ struct ConvKernelParams {
   __half* out2_h;
   const float* scale2;
   const float* shift2;
+  // EPI kernels without HALO: row-softmax passes (WFK_ACT_ROW_MAX / ROW_EXP / ROW_NORM), [rows][row_ld] fp32 partials
+  const float* row_in;
+  float* row_out;
+  int row_ld;
+  float row_scale;
   uint32_t idesc;
   // Cout = 128 HALO kernel (MB = 2): 16-bit output through TMA stores. (c, x, y, frame) view of the NHWC output, box
   // 32 channels x 8 x 4 pixels = one epilogue warp's chunk, 64-byte swizzle = the warp's staging-tile layout.
@@ -137,6 +142,12 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
   t.ty = r / p.tiles_x;
   t.tx = r - t.ty * p.tiles_x;
   return t;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // Epilogue activations of the EPI kernels (wfk_act in the C ABI).
@@ -238,6 +249,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
   // The 256-wide HALO kernel does the same with its 16-row staging tile (two 1 KB stores per chunk): its epilogue is not
   // critical, but the LDS / STG / address work it no longer does is shared-memory bandwidth and power returned to the MMAs.
   constexpr bool kTmaStore = HALO && !EPI;
+  constexpr bool kRowModes = EPI && !HALO;         // row-softmax epilogues (attention GEMMs)
   constexpr uint32_t kStageWarpBytes = HALO ? 2048u / kStPasses : 4096u;
   constexpr int kBRows = PAIR ? BN / 2 : BN;       // weight rows this CTA stages
   constexpr int kBBytes = kBRows * kBlockK * 2;
@@ -830,6 +842,7 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
       // output coordinates of this thread's row in each of this CTA's MB pixel blocks
       bool valid_mb[2] = {false, false};
       int64_t base_mb[2] = {0, 0};
+      [[maybe_unused]] int64_t pix_mb[2] = {0, 0};
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
         const int blk = static_cast<int>(cta_rank) * MB + mb;
@@ -842,6 +855,28 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
         const int ox = px * p.out_sx + (t.phase & 1);
         const int64_t pix = (static_cast<int64_t>(t.frame) * p.out_rows + oy) * p.out_cols + ox;
         base_mb[mb] = pix * p.ldc + static_cast<int64_t>(t.nt) * BN;
+        pix_mb[mb] = pix;
+      }
+      // Row-softmax passes: this thread's row operand (ROW_EXP: -max * scale, ROW_NORM: 1 / sum; the slots are folded in
+      // a fixed order) and its running max / sum over the tile's columns.
+      [[maybe_unused]] float row_a[2] = {0.f, 0.f};
+      [[maybe_unused]] float row_r[2] = {0.f, 0.f};
+      if constexpr (kRowModes) {
+        if (p.act >= WFK_ACT_ROW_MAX) {
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            row_r[mb] = (p.act == WFK_ACT_ROW_MAX) ? -INFINITY : 0.f;
+            if (p.act != WFK_ACT_ROW_MAX && valid_mb[mb]) {
+              const float* rp = p.row_in + pix_mb[mb] * p.row_ld;
+              float a = (p.act == WFK_ACT_ROW_EXP) ? -INFINITY : 0.f;
+              for (int i = 0; i < p.row_ld; ++i) {
+                const float x = __ldg(rp + i);
+                a = (p.act == WFK_ACT_ROW_EXP) ? fmaxf(a, x) : a + x;
+              }
+              row_a[mb] = (p.act == WFK_ACT_ROW_EXP) ? -a * p.row_scale : 1.f / a;
+            }
+          }
+        }
       }
       const int ncols = min(BN, p.n_total - t.nt * BN);  // N tail: columns >= ncols are padding
       const int nchunks = (ncols + 31) >> 5;
@@ -1024,7 +1059,27 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           }
         }
         if constexpr (EPI) {
-          if (p.act != 0) {
+          if (kRowModes && p.act >= WFK_ACT_ROW_MAX) {
+            const int nv = ncols - c0;   // valid columns of this chunk (the accumulators beyond hold zero-filled padding)
+            const float ra = (MB == 1) ? row_a[0] : (mb ? row_a[1] : row_a[0]);
+            float rr = (MB == 1) ? row_r[0] : (mb ? row_r[1] : row_r[0]);
+            if (p.act == WFK_ACT_ROW_MAX) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) rr = fmaxf(rr, i < nv ? v[i] : -INFINITY);
+            } else if (p.act == WFK_ACT_ROW_EXP) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float e = i < nv ? ex2_approx(fmaf(v[i], p.row_scale, ra)) : 0.f;
+                v[i] = e;
+                rr += e;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], ra, s_sh2[c0 + i]);
+            }
+            if (MB == 1 || mb == 0) row_r[0] = rr;
+            else row_r[1] = rr;
+          } else if (p.act != 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = act_apply(p.act, v[i], p.act_slope);
           }
@@ -1162,6 +1217,13 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
           }
         }
       }  // chunk loop
+      if constexpr (kRowModes) {
+        if (p.act >= WFK_ACT_ROW_MAX && p.row_out != nullptr) {   // one (row, slot) per thread and block
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb)
+            if (valid_mb[mb]) p.row_out[pix_mb[mb] * p.row_ld + t.nt * kParts + part] = row_r[mb];
+        }
+      }
       // accumulator drained: hand the TMEM buffer back to the MMA warp (of the leader CTA when PAIR)
       tc_fence_before();
       __syncwarp();
@@ -1424,8 +1486,18 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   WFK_REQUIRE(d->taps_per_phase >= 1 && d->num_phases * d->taps_per_phase <= WFK_MAX_TAPS, "too many taps");
   WFK_REQUIRE(d->n_frames >= 1 && d->tile_h >= 1 && d->tile_w >= 1, "empty problem");
   WFK_REQUIRE(d->a[0].ptr != nullptr && d->b[0].ptr != nullptr, "A/B source 0 missing");
-  WFK_REQUIRE(d->out_h != nullptr || d->out_f != nullptr || d->out2_h != nullptr, "no output requested");
-  WFK_REQUIRE(d->act >= 0 && d->act <= WFK_ACT_SILU && d->act2 >= 0 && d->act2 <= WFK_ACT_SILU, "unknown activation");
+  WFK_REQUIRE(d->out_h != nullptr || d->out_f != nullptr || d->out2_h != nullptr ||
+                  (d->act == WFK_ACT_ROW_MAX && d->row_out != nullptr),
+              "no output requested");
+  WFK_REQUIRE(d->act >= 0 && d->act <= WFK_ACT_ROW_NORM && d->act2 >= 0 && d->act2 <= WFK_ACT_SILU, "unknown activation");
+  if (d->act >= WFK_ACT_ROW_MAX) {
+    WFK_REQUIRE(d->act == WFK_ACT_ROW_NORM || d->row_out != nullptr, "ROW_MAX / ROW_EXP need row_out");
+    WFK_REQUIRE(d->act == WFK_ACT_ROW_MAX || d->row_in != nullptr, "ROW_EXP / ROW_NORM need row_in");
+    WFK_REQUIRE(d->act != WFK_ACT_ROW_EXP || d->out_h != nullptr, "ROW_EXP writes its values to out_h");
+    WFK_REQUIRE(d->residual == nullptr && d->stats == nullptr && d->out2_h == nullptr && d->num_phases == 1 &&
+                    d->taps_per_phase == 1,
+                "row-softmax epilogues take plain one-tap GEMM descriptors");
+  }
   WFK_REQUIRE(d->ldc % 8 == 0, "ldc must be a multiple of 8");
   bool uses_src1 = false;
   for (int i = 0; i < d->num_phases * d->taps_per_phase; ++i) {
@@ -1534,6 +1606,10 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   p.out2_h = static_cast<__half*>(d->out2_h);
   p.scale2 = d->scale2;
   p.shift2 = d->shift2;
+  p.row_in = d->row_in;
+  p.row_out = d->row_out;
+  p.row_ld = d->row_ld;
+  p.row_scale = d->row_scale;
   plan->epi = (d->act != 0 || d->out2_h != nullptr) ? 1 : 0;
   plan->bf16 = d->operand_bf16 ? 1 : 0;
   if (plan->bf16 && (plan->epi || !plan->pair)) {
@@ -1543,6 +1619,13 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
   if (plan->epi && !plan->pair) {
     delete plan;
     return wfk::fail(WFK_ERR_INVALID, "activation epilogues need the CTA-pair kernels (WFK_CONV_PAIR=0 is set)");
+  }
+  // ROW_MAX / ROW_EXP write one slot per (N tile, epilogue half); ROW_NORM only reads the producer's slots
+  if (d->act >= WFK_ACT_ROW_MAX &&
+      (plan->halo || d->row_ld < 1 || (d->act != WFK_ACT_ROW_NORM && d->row_ld != 2 * p.tiles_n))) {
+    delete plan;
+    return wfk::fail(WFK_ERR_INVALID, "row-softmax epilogue: row_ld=%d must be 2 * ceil(n_total / %d) = %d (and no 3x3 taps)",
+                     d->row_ld, plan->bn, 2 * p.tiles_n);
   }
   p.cpg_log2 = cpg_log2;
   p.groups_total = d->stats ? (d->n_total >> cpg_log2) : 0;

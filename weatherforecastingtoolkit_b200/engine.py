@@ -272,6 +272,9 @@ class AKLEngine:
         self.gn_inline = os.environ.get("WFK_GN_INLINE", "0") != "0"
         self.res_as_mma = os.environ.get("WFK_RES_AS_MMA", "1") != "0"
         self.stem_tc = os.environ.get("WFK_STEM_TC", "1") != "0"   # tensor-core stem kernels (A/B switch)
+        # 1: three-pass softmax attention without the fp32 score matrix (see _Program.attention); measured equal to the
+        # default chain within noise on B200, so it stays an opt-in
+        self.attn_fused = os.environ.get("WFK_ATTN_FUSED", "0") == "1"
         self.attn_group = int(os.environ.get("WFK_ATTN_GROUP", "0"))   # frames per attention group (0: all frames at once)
         if self.bf16 and not (self.fuse_gn and self.stem_tc):
             raise ValueError("bf16 operands need the default kernel set (fused GroupNorm, tensor-core stems)")
@@ -639,19 +642,32 @@ class _Program:
         self._epilogue(d, None, None, vt, None, None, 1, c, T)
         self._conv_plan(d, p + ".value^T", 2.0 * n * T * c * c)
         self.pool.put(a)
-        # scores = Q K^T (fp32) -> row softmax -> O = P V (+ value bias). The chain can run in groups of `ag` frames so
-        # that the fp32 scores (21 MB per frame at 2304 tokens) and the probabilities of a group stay in the 126 MB L2
-        # instead of streaming 63 MB per frame through HBM (WFK_ATTN_GROUP). Measured on B200 (same box, bench.py):
-        # all 37 frames at once 314.7 frames/s; groups of 4 / 3 / 2 / 1 frames 312.8 / 311.0 / 309.5 / 303.2 -- the extra
-        # launches and the partial last wave of 162-tile GEMMs cost more than the HBM traffic they save, so the default
-        # is one group.
+        # scores = Q K^T (fp32) -> row softmax -> O = P V (+ value bias): three launches, 63 MB of score / probability
+        # traffic per frame at 2304 tokens.
+        # Opt-in alternative (WFK_ATTN_FUSED=1, fp16 operands) that never materialises the fp32 scores: pass 1 computes
+        # Q K^T and keeps only the row maxima, pass 2 computes it AGAIN and writes exp(s - max) as 16-bit values plus
+        # fp32 row sums, pass 3 is P V with the 1 / sum scaling and the value bias in its epilogue (WFK_ACT_ROW_* in
+        # include/wfk_b200.h). Measured on one B200, same box, bench.py (frames/s, alternating): fused 324.1 / 323.4,
+        # default 324.6 / 324.0. Per 37 frames: default 322 + 276 + 172 us (scores, softmax, P V); fused 249 + 563 +
+        # 172 us -- a K = 512 tile gives the tensor pipe only ~2700 cycles of work, while 128 x 256 exponentials cost
+        # the SM's 16 MUFU lanes 2048 cycles before any packing or storing, so the exp pass is epilogue-bound (and a
+        # single-kernel flash attention has the same exp-per-MMA ratio plus O = 128 x 512 fp32 filling all of TMEM).
+        # Both chains can run in groups of `ag` frames (WFK_ATTN_GROUP); measured: all 37 frames at once 314.7
+        # frames/s, groups of 4 / 3 / 2 / 1 frames 312.8 / 311.0 / 309.5 / 303.2 -- the extra launches and partial
+        # last waves cost more than the L2 residency saves, so the default is one group.
         o = self.pool.get((n, T, c))
         ag = max(1, min(n, self.eng.attn_group if self.eng.attn_group > 0 else n))
-        scores = self.pool.get((ag, T, T), torch.float32)
+        fused = not self.bf and self.eng.attn_fused
         probs = self.pool.get((ag, T, T))
         esz = 2
-        for g0 in range(0, n, ag):
-            ng = min(ag, n - g0)
+        if fused:
+            slots = 2 * ((T + 255) // 256) if (T % 256 == 0 or T > 256) else 2 * ((T + 127) // 128)   # 2 per N tile
+            rmax = self.pool.get((ag, T, slots), torch.float32)
+            rsum = self.pool.get((ag, T, slots), torch.float32)
+        else:
+            scores = self.pool.get((ag, T, T), torch.float32)
+
+        def qk_desc(g0, ng):
             d = ConvDesc()
             self._view_nhwc(d.a[0], qk[g0:], ng, 1, T, c, pitch_c=2 * c)
             kview = qk[g0:].reshape(-1)[c:]
@@ -660,10 +676,27 @@ class _Program:
             d.num_phases, d.taps_per_phase = 1, 1
             d.taps[0] = Tap(0, 0, 0, 0, 0, 0, c // 64, 0)
             d.a_frame_mul, d.b_frame_mul = 1, 1
-            self._epilogue(d, None, None, None, scores, None, 1, T, T)
-            self._conv_plan(d, p + ".scores", 2.0 * ng * T * T * c)
-            self._add(self.lib.wfk_softmax_rows,
-                      (scores.data_ptr(), ng * T, T, 1.0 / math.sqrt(c), probs.data_ptr(), self.bf), p + ".softmax")
+            return d
+
+        for g0 in range(0, n, ag):
+            ng = min(ag, n - g0)
+            fl = 2.0 * ng * T * T * c
+            if fused:
+                d = qk_desc(g0, ng)
+                self._epilogue(d, None, None, None, None, None, 1, T, T)
+                d.act, d.row_out, d.row_ld = _cabi.ACT_ROW_MAX, rmax.data_ptr(), slots
+                self._conv_plan(d, p + ".scores(max)", 0.0, fl)
+                d = qk_desc(g0, ng)
+                self._epilogue(d, None, None, probs, None, None, 1, T, T)
+                d.act, d.row_in, d.row_out, d.row_ld = _cabi.ACT_ROW_EXP, rmax.data_ptr(), rsum.data_ptr(), slots
+                d.row_scale = math.log2(math.e) / math.sqrt(c)
+                self._conv_plan(d, p + ".scores(exp)", fl, fl)
+            else:
+                d = qk_desc(g0, ng)
+                self._epilogue(d, None, None, None, scores, None, 1, T, T)
+                self._conv_plan(d, p + ".scores", fl)
+                self._add(self.lib.wfk_softmax_rows,
+                          (scores.data_ptr(), ng * T, T, 1.0 / math.sqrt(c), probs.data_ptr(), self.bf), p + ".softmax")
             d = ConvDesc()
             self._view_nhwc(d.a[0], probs, ng, 1, T, T)
             self._view_w(d.b[0], vt[g0:], T, c, ng)
@@ -671,10 +704,19 @@ class _Program:
             d.num_phases, d.taps_per_phase = 1, 1
             d.taps[0] = Tap(0, 0, 0, 0, 0, 0, (T + 63) // 64, 0)
             d.a_frame_mul, d.b_frame_mul = 1, 1
-            self._epilogue(d, t[p + ".value.bias"], None, o[g0:], None, None, 1, T, c)
-            self._conv_plan(d, p + ".pv", 2.0 * ng * T * T * c)
+            if fused:
+                self._epilogue(d, None, None, o[g0:], None, None, 1, T, c)
+                d.act, d.row_in, d.row_ld = _cabi.ACT_ROW_NORM, rsum.data_ptr(), slots
+                d.shift2 = t[p + ".value.bias"].data_ptr()
+            else:
+                self._epilogue(d, t[p + ".value.bias"], None, o[g0:], None, None, 1, T, c)
+            self._conv_plan(d, p + ".pv", fl)
         self.pool.put(qk)
-        self.pool.put(scores)
+        if fused:
+            self.pool.put(rmax)
+            self.pool.put(rsum)
+        else:
+            self.pool.put(scores)
         self.pool.put(probs)
         self.pool.put(vt)
         # proj + residual
