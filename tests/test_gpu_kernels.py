@@ -350,7 +350,11 @@ def test_nhwc_to_nchw_f32(lib):
 # ------------------------------------------------------------------ tensor-core stem convolutions
 @pytest.mark.parametrize("n,cin,h,w,cout,ones,cpg", [(2, 1, 64, 64, 128, 0, 4), (1, 1, 50, 70, 128, 0, 4),
                                                       (2, 4, 48, 48, 512, 1, 16), (1, 4, 13, 9, 256, 1, 8),
-                                                      (1, 3, 20, 24, 128, 0, 8)])
+                                                      (1, 3, 20, 24, 128, 0, 8),
+                                                      # single-plane lean kernel (w % 16 == 0): every group size, several
+                                                      # rows per warp, two 128-channel chunks, the production frame
+                                                      (1, 1, 32, 48, 256, 0, 8), (2, 1, 16, 16, 128, 0, 16),
+                                                      (1, 1, 7, 16, 128, 0, 4), (1, 1, 384, 384, 128, 0, 4)])
 def test_stem_tc_vs_conv2d(lib, n, cin, h, w, cout, ones, cpg):
     """wfk_conv3x3_stem_tc == conv3x3(pad 1) of (optionally) a 1x1 pre-convolution, on identical fp16 operands;
     GroupNorm sums of the fp32 result."""

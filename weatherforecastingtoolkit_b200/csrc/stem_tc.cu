@@ -179,6 +179,162 @@ __global__ void __launch_bounds__(kStemTcThreads, KSTEPS == 1 ? 5 : 3) conv3x3_s
   }
 }
 
+// Single-plane variant (encoder.conv_in: 1 -> cout at 384^2, 37.7 MB of output per frame), for widths that are a
+// multiple of 16 so that a 16-pixel M tile is a run of one image row. The generic kernel above spends ~900 instructions
+// per tile (per-lane im2col addressing with bounds checks, scalar GroupNorm sums, a staged store) and runs at 3x the
+// HBM time of the layer; this one needs ~200:
+//  * the 3 x 18 input patch of a tile is loaded by 18 lanes (coalesced, one predicated load per row), parked as 16-bit
+//    values in a double-buffered shared-memory patch, and every lane reads its A-fragment taps from fixed offsets;
+//  * the bias rides through the tensor core: rows k = 9, 10, 11 of the weight fragment hold its hi / lo / lo2 16-bit
+//    split (>= 24 significant bits) against constant-one A columns;
+//  * MMA column n of n-tile nt maps to channel (nt>>2)*32 + (n>>1)*8 + (nt&3)*2 + (n&1): a lane's accumulators of four
+//    consecutive n-tiles are 8 CONTIGUOUS channels, i.e. one 128-bit store per pixel row straight from registers (the
+//    four lanes of a pixel cover 64 contiguous bytes: full 32-byte sectors, no staging tile);
+//  * GroupNorm partial sums with packed fp32x2 adds / FMAs.
+template <bool BF16>
+__global__ void __launch_bounds__(kStemTcThreads, 4) conv3x3_stem1_tc_kernel(
+    const float* __restrict__ in, int h, int w, const uint16_t* __restrict__ wt, const float* __restrict__ bias, int cout,
+    uint16_t* __restrict__ out, double* __restrict__ stats, int cpg, int tiles_per_warp) {
+  constexpr int kPatchPitch = 24;
+  __shared__ uint2 s_bf[16][32];
+  __shared__ uint16_t s_patch[kStemTcWarps][2][3 * kPatchPitch];
+  __shared__ float s_stats[kStemTcWarps][kStemTcN / 4][2];
+  const int n = blockIdx.y, chunk = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int hw = h * w;
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int ln = i & 31, nt = i >> 5;
+    const int nn = ln >> 2;
+    const int col = chunk * kStemTcN + (nt >> 2) * 32 + (nn >> 1) * 8 + (nt & 3) * 2 + (nn & 1);
+    const int k0 = (ln & 3) * 2;
+    auto wrow = [&](int k) -> uint32_t {
+      if (k < 9) return wt[static_cast<int64_t>(k) * cout + col];
+      if (k > 11) return 0u;
+      // bias = hi + lo + lo2, each exactly representable in the 16-bit operand format
+      float r = bias[col];
+      uint16_t part = A16<BF16>::pack1(r);
+      for (int j = 9; j < k; ++j) {
+        r -= A16<BF16>::unpack1(part);
+        part = A16<BF16>::pack1(r);
+      }
+      return part;
+    };
+    s_bf[nt][ln] = make_uint2(wrow(k0) | (wrow(k0 + 1) << 16), wrow(k0 + 8) | (wrow(k0 + 9) << 16));
+  }
+  for (int i = threadIdx.x; i < kStemTcWarps * (kStemTcN / 4) * 2; i += blockDim.x) (&s_stats[0][0][0])[i] = 0.f;
+  __syncthreads();
+  // fixed patch offsets of this lane's taps: k = 2t, 2t+1 (a0 / a1) and k = 8 (a2 / a3 of t == 0); patch column 0 is x0-1
+  const int o0 = ((2 * t) / 3) * kPatchPitch + (2 * t) % 3 + g;
+  const int o1 = ((2 * t + 1) / 3) * kPatchPitch + (2 * t + 1) % 3 + g;
+  const int o8 = 2 * kPatchPitch + 2 + g;
+  const uint32_t one16 = A16<BF16>::pack1(1.f);
+  // a2 / a3 upper halves and constants: t == 0: {tap 8, 1}; t == 1: {1, 1}; t >= 2: 0
+  const uint32_t a23_const = (t == 0) ? (one16 << 16) : (t == 1 ? (one16 | (one16 << 16)) : 0u);
+  const float* inn = in + static_cast<int64_t>(n) * hw;
+  float2 gs[8], gq[8];   // slot = (nt >> 2) * 2 + ((nt & 3) >> 1): 4 contiguous channels of this lane
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gs[i] = gq[i] = make_float2(0.f, 0.f);
+  const int mtiles = hw >> 4;
+  const int mt0 = (blockIdx.x * kStemTcWarps + warp) * tiles_per_warp;
+  const int mt_end = min(mt0 + tiles_per_warp, mtiles);
+  int y = (mt0 * 16) / w, x0 = mt0 * 16 - y * w;
+  auto load_patch = [&](int yy, int xx, float (&v)[3]) {
+    const int col = xx - 1 + lane;
+    const bool cok = lane < 18 && col >= 0 && col < w;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int row = yy - 1 + r;
+      v[r] = (cok && row >= 0 && row < h) ? __ldg(inn + row * w + col) : 0.f;
+    }
+  };
+  float v[3] = {0.f, 0.f, 0.f};
+  if (mt0 < mt_end) load_patch(y, x0, v);
+  uint16_t* outp = out + (static_cast<int64_t>(n) * hw + mt0 * 16 + g) * cout + chunk * kStemTcN + t * 8;
+  const int64_t row8 = static_cast<int64_t>(8) * cout;
+  for (int mt = mt0; mt < mt_end; ++mt) {
+    uint16_t* pb = s_patch[warp][mt & 1];
+    if (lane < 18) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) pb[r * kPatchPitch + lane] = A16<BF16>::pack1(v[r]);
+    }
+    // next tile's patch: in flight during this tile's MMAs and stores
+    x0 += 16;
+    if (x0 == w) {
+      x0 = 0;
+      ++y;
+    }
+    if (mt + 1 < mt_end) load_patch(y, x0, v);
+    __syncwarp();
+    uint32_t a[4];
+    a[0] = pb[o0] | (static_cast<uint32_t>(pb[o1]) << 16);
+    a[1] = pb[o0 + 8] | (static_cast<uint32_t>(pb[o1 + 8]) << 16);
+    a[2] = a23_const | (t == 0 ? static_cast<uint32_t>(pb[o8]) : 0u);
+    a[3] = a23_const | (t == 0 ? static_cast<uint32_t>(pb[o8 + 8]) : 0u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        const uint2 b = s_bf[q * 4 + j][lane];
+        mma_16816<BF16>(acc[j], a, b.x, b.y);
+      }
+      uint4 lo, hi;
+      uint32_t* lo32 = reinterpret_cast<uint32_t*>(&lo);
+      uint32_t* hi32 = reinterpret_cast<uint32_t*>(&hi);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 c01 = make_float2(acc[j][0], acc[j][1]), c23 = make_float2(acc[j][2], acc[j][3]);
+        const int slot = q * 2 + (j >> 1);
+        gs[slot] = __fadd2_rn(gs[slot], __fadd2_rn(c01, c23));
+        gq[slot] = __ffma2_rn(c01, c01, gq[slot]);
+        gq[slot] = __ffma2_rn(c23, c23, gq[slot]);
+        lo32[j] = A16<BF16>::pack(c01.x, c01.y);
+        hi32[j] = A16<BF16>::pack(c23.x, c23.y);
+      }
+      *reinterpret_cast<uint4*>(outp + q * 32) = lo;
+      *reinterpret_cast<uint4*>(outp + row8 + q * 32) = hi;
+    }
+    outp += static_cast<int64_t>(16) * cout;
+  }
+  if (stats != nullptr) {
+    // lanes that differ in g hold other pixels of the same channels: fold lane bits 2..4; then the lane's 8 slots of
+    // 4 channels each are combined according to the group size (cpg 8: two slots; cpg 16: also lanes t, t^1)
+#pragma unroll
+    for (int slot = 0; slot < 8; ++slot) {
+      float s = gs[slot].x + gs[slot].y, q = gq[slot].x + gq[slot].y;
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (cpg == 16) {
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+      }
+      // channel of this slot inside the chunk: (slot >> 1) * 32 + t * 8 + (slot & 1) * 4
+      const int gl = ((slot >> 1) * 32 + t * 8 + (slot & 1) * 4) / cpg;
+      const bool writer = g == 0 && (cpg != 16 || (t & 1) == 0);
+      if (writer) {  // this warp's private slots; for cpg >= 8 the two slots of a group are added one after the other
+        s_stats[warp][gl][0] += s;
+        s_stats[warp][gl][1] += q;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    const int groups_chunk = kStemTcN / cpg;
+    if (threadIdx.x < 2 * groups_chunk) {
+      const int gl = threadIdx.x >> 1, m = threadIdx.x & 1;
+      float tot = 0.f;
+#pragma unroll
+      for (int wi = 0; wi < kStemTcWarps; ++wi) tot += s_stats[wi][gl][m];
+      const int groups = cout / cpg;
+      atomicAdd(&stats[(static_cast<int64_t>(n) * groups + chunk * groups_chunk + gl) * 2 + m], static_cast<double>(tot));
+    }
+  }
+}
+
 }  // namespace wfk
 
 extern "C" int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w, int ones_plane, const void* weight_h,
@@ -192,14 +348,26 @@ extern "C" int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w
   if (stats) WFK_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16, "cpg=%d unsupported (4, 8, 16)", cpg);
   const int ksteps = (K + 15) / 16;
   const int mtiles = (h * w + 15) / 16;
-  int tpw = 8;
-  while (tpw > 1 && static_cast<int64_t>((mtiles + wfk::kStemTcWarps * tpw - 1) / (wfk::kStemTcWarps * tpw)) * n * (cout / wfk::kStemTcN) <
-                        4 * static_cast<int64_t>(wfk::num_sms()))
-    tpw >>= 1;
+  // ONE wave of blocks: a block's prologue (weight-fragment table built from 16-bit global loads) costs as much as
+  // ~10 tiles of work, so with a few tiles per warp it dominated both kernels (measured: encoder.conv_in 449 us for 37
+  // frames with 8 tiles per warp, 336 us with one wave; the tile loop itself is ~1/3 of that).
+  const bool lean = cin == 1 && !ones_plane && w % 16 == 0 && static_cast<int64_t>(h) * w < (1 << 30);
+  const int resident = lean ? 4 : (ksteps == 1 ? 5 : 3);   // blocks per SM (the kernels' __launch_bounds__)
+  const int64_t slots = resident * static_cast<int64_t>(wfk::num_sms());
+  const int64_t per_frame = slots / (static_cast<int64_t>(n) * (cout / wfk::kStemTcN));
+  const int bpf = static_cast<int>(per_frame < 1 ? 1 : per_frame);   // blocks per (frame, 128-channel chunk)
+  const int tpw = (mtiles + wfk::kStemTcWarps * bpf - 1) / (wfk::kStemTcWarps * bpf);
   dim3 grid((mtiles + wfk::kStemTcWarps * tpw - 1) / (wfk::kStemTcWarps * tpw), n, cout / wfk::kStemTcN);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint16_t* wh = static_cast<const uint16_t*>(weight_h);
   uint16_t* oh = static_cast<uint16_t*>(out);
+  if (lean) {   // single input plane, 16-pixel tiles inside one image row
+    if (bf16)
+      wfk::conv3x3_stem1_tc_kernel<true><<<grid, wfk::kStemTcThreads, 0, s>>>(in, h, w, wh, bias, cout, oh, stats, cpg, tpw);
+    else
+      wfk::conv3x3_stem1_tc_kernel<false><<<grid, wfk::kStemTcThreads, 0, s>>>(in, h, w, wh, bias, cout, oh, stats, cpg, tpw);
+    return wfk::launched("conv3x3_stem1_tc_kernel");
+  }
 #define WFK_STEM_LAUNCH(KS, BF) \
   wfk::conv3x3_stem_tc_kernel<KS, BF><<<grid, wfk::kStemTcThreads, 0, s>>>(in, cin, ones_plane, h, w, wh, bias, cout, oh, stats, cpg, tpw)
   if (bf16) {
