@@ -395,6 +395,34 @@ def test_stem_tc_vs_conv2d(lib, n, cin, h, w, cout, ones, cpg):
         assert rel_l2(out.float(), want32) < 5e-3
 
 
+# ------------------------------------------------------------------ decoder tail: GroupNorm + SiLU + conv3x3(C -> 1)
+@pytest.mark.parametrize("n,h,w,c,groups", [(2, 40, 72, 128, 32), (1, 16, 16, 128, 32), (1, 21, 35, 64, 32),
+                                             (1, 33, 18, 256, 32), (1, 96, 160, 128, 32)])
+def test_gn_silu_conv3x3_c1_vs_fp32(lib, n, h, w, c, groups):
+    """wfk_gn_silu_conv3x3_c1 (vae.py:162-164: conv_norm_out, SiLU, conv_out) against F.group_norm / F.silu /
+    F.conv2d in fp32 on the same fp16 input: interior tiles (table addressing), border tiles and ragged sizes."""
+    from weatherforecastingtoolkit_b200 import _cabi
+    torch.manual_seed(h * 100 + w + c)
+    x = (torch.randn(n, h, w, c) * 1.5 + 0.3).half()
+    gamma, beta = torch.randn(c) * 0.5 + 1.0, torch.randn(c) * 0.3
+    wt = torch.randn(1, c, 3, 3) / math.sqrt(9 * c)
+    bias = 0.1
+    xf = x.float().permute(0, 3, 1, 2)
+    cpg = c // groups
+    gsum = xf.double().reshape(n, groups, cpg * h * w)
+    stats = torch.stack([gsum.sum(-1), (gsum * gsum).sum(-1)], dim=-1).contiguous()
+    want = F.conv2d(F.silu(F.group_norm(xf, groups, gamma, beta, 1e-6)), wt, torch.tensor([bias]), padding=1)
+    out = torch.empty(n, 1, h, w, device=DEV)
+    xd, sd, gd, bd = x.to(DEV), stats.to(DEV), gamma.to(DEV), beta.to(DEV)
+    wd = wt[0].permute(1, 2, 0).reshape(9, c).contiguous().to(DEV)          # [tap][c] fp32
+    _cabi.check(lib.wfk_gn_silu_conv3x3_c1(xd.data_ptr(), sd.data_ptr(), gd.data_ptr(), bd.data_ptr(), n, h, w, c, groups,
+                                           1e-6, wd.data_ptr(), bias, out.data_ptr(), 0,
+                                           torch.cuda.current_stream().cuda_stream), "tail")
+    torch.cuda.synchronize()
+    assert rel_l2(out, want) < 2e-3
+    assert (out.cpu() - want).abs().max().item() < 2e-2
+
+
 # ------------------------------------------------------------------ event windowing + staging (SURVEY 8f.2)
 def test_stage_vil_windows_bitexact(lib):
     """Windows cut from resident uint8 events == the reference's slicing (sevir.py:879-889) + staging formula."""
