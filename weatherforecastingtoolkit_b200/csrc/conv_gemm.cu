@@ -826,7 +826,10 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
         if (stats_frame >= 0) flush_reg_stats(stats_frame);
         stats_frame = t.frame;
       }
-      if (t.nt != bias_nt) {  // stage this N tile's bias once (smem broadcast reads in the chunk loop)
+      // stage this N tile's bias once (smem broadcast reads in the chunk loop). Without any per-channel vector (attention
+      // scores: nine N tiles per pixel block, i.e. a new N tile -- and two barriers over the 256 epilogue threads -- on
+      // EVERY tile) the zeros / ones staged for the first tile stay valid.
+      if (t.nt != bias_nt && (bias_nt < 0 || p.bias != nullptr || (EPI && (p.scale2 != nullptr || p.shift2 != nullptr)))) {
         named_bar_sync(2, kEpiThreads);
         for (int i = et; i < BN; i += kEpiThreads) {
           const int c = t.nt * BN + i;
