@@ -324,7 +324,8 @@ def test_metrics_deterministic(lib):
 
 
 # ------------------------------------------------------------------ row softmax (attention.py:171)
-@pytest.mark.parametrize("rows,cols", [(37, 2304), (5, 4096), (9, 50), (3, 4100)])
+@pytest.mark.parametrize("rows,cols", [(37, 2304), (5, 4096), (9, 50), (3, 4100), (13, 256), (21, 1024), (8, 2048),
+                                       (2 * 2304, 2304)])
 def test_softmax_rows(lib, rows, cols):
     from weatherforecastingtoolkit_b200 import _cabi
     torch.manual_seed(rows + cols)

@@ -648,8 +648,8 @@ class _Program:
         # Q K^T and keeps only the row maxima, pass 2 computes it AGAIN and writes exp(s - max) as 16-bit values plus
         # fp32 row sums, pass 3 is P V with the 1 / sum scaling and the value bias in its epilogue (WFK_ACT_ROW_* in
         # include/wfk_b200.h). Measured on one B200, same box, bench.py (frames/s, alternating): fused 324.1 / 323.4,
-        # default 324.6 / 324.0. Per 37 frames: default 322 + 276 + 172 us (scores, softmax, P V); fused 249 + 563 +
-        # 172 us -- a K = 512 tile gives the tensor pipe only ~2700 cycles of work, while 128 x 256 exponentials cost
+        # default 324.6 / 324.0. Per 37 frames: default 322 + 276 + 172 us (scores, softmax, P V; since then 270 + 179 +
+        # 172 us); fused 249 + 563 + 172 us -- a K = 512 tile gives the tensor pipe only ~2700 cycles of work, while 128 x 256 exponentials cost
         # the SM's 16 MUFU lanes 2048 cycles before any packing or storing, so the exp pass is epilogue-bound (and a
         # single-kernel flash attention has the same exp-per-MMA ratio plus O = 128 x 512 fp32 filling all of TMEM).
         # Both chains can run in groups of `ag` frames (WFK_ATTN_GROUP); measured: all 37 frames at once 314.7
