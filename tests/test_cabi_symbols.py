@@ -34,7 +34,12 @@ def test_binding_covers_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.wfk_abi_version() == 3
+    from weatherforecastingtoolkit_b200 import _cabi
+    assert lib.wfk_abi_version() == _cabi.ABI_VERSION == 3
+    # the header, the library and the ctypes mirror must move together
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "wfk_b200.h")).read()
+    assert int(re.search(r"#define WFK_ABI_VERSION (\d+)", hdr).group(1)) == _cabi.ABI_VERSION
     assert lib.wfk_strerror(0) == b"ok"
     assert b"invalid" in lib.wfk_strerror(-1)
 

@@ -15,6 +15,7 @@ _LIB_PATH = Path(os.environ.get("WFK_LIB_PATH") or (Path(__file__).resolve().par
 WFK_MAX_THRESHOLDS = 8
 WFK_NUM_POOLS = 3
 WFK_MAX_TAPS = 40
+ABI_VERSION = 3          # WFK_ABI_VERSION of include/wfk_b200.h these bindings mirror
 
 
 class MetricPartials(C.Structure):
@@ -156,6 +157,10 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        got = lib.wfk_abi_version()
+        if got != ABI_VERSION:   # a stale library would read the ctypes mirrors of the structs with the wrong layout
+            raise RuntimeError(f"{_LIB_PATH} has ABI version {got}, the Python bindings expect {ABI_VERSION}: rebuild it "
+                               "with `python -m weatherforecastingtoolkit_b200.build --force`")
         _lib = lib
     return _lib
 
