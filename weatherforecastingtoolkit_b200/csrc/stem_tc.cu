@@ -7,6 +7,8 @@
 // [K x 128] weight fragments live in shared memory, and one warp produces 16 pixels x 128 channels per step.
 // The CUDA-core kernels they replace (edge_convs.cu / in_conv.cu) needed 9*cin FMAs per output value and ran 5-13x
 // above the HBM time of the layer. Also accumulates the GroupNorm (sum, sum of squares) of the fp32 result.
+#include <cstdlib>
+
 #include "act16.cuh"
 #include "internal.h"
 
@@ -351,7 +353,8 @@ extern "C" int wfk_conv3x3_stem_tc(const float* in, int n, int cin, int h, int w
   // ONE wave of blocks: a block's prologue (weight-fragment table built from 16-bit global loads) costs as much as
   // ~10 tiles of work, so with a few tiles per warp it dominated both kernels (measured: encoder.conv_in 449 us for 37
   // frames with 8 tiles per warp, 336 us with one wave; the tile loop itself is ~1/3 of that).
-  const bool lean = cin == 1 && !ones_plane && w % 16 == 0 && static_cast<int64_t>(h) * w < (1 << 30);
+  static const bool lean_enabled = !(std::getenv("WFK_STEM_LEAN") && std::getenv("WFK_STEM_LEAN")[0] == '0');   // A/B switch
+  const bool lean = lean_enabled && cin == 1 && !ones_plane && w % 16 == 0 && static_cast<int64_t>(h) * w < (1 << 30);
   const int resident = lean ? 4 : (ksteps == 1 ? 5 : 3);   // blocks per SM (the kernels' __launch_bounds__)
   const int64_t slots = resident * static_cast<int64_t>(wfk::num_sms());
   const int64_t per_frame = slots / (static_cast<int64_t>(n) * (cout / wfk::kStemTcN));
