@@ -70,6 +70,9 @@ CONV_CASES = [
     ("residual", 2, 24, 40, 256, 512), ("shortcut", 1, 32, 32, 128, 256), ("shortcut", 2, 8, 8, 512, 256),
     ("down", 2, 32, 48, 128, 128), ("down", 1, 6, 6, 512, 512), ("up", 1, 24, 24, 256, 256),
     ("up", 2, 5, 7, 512, 512), ("residual", 2, 96, 96, 512, 512), ("plain", 1, 384, 384, 128, 128),
+    # fused upsample with whole 16-row tiles: the sub-pixel phases leave through 5-D TMA stores (two frames: the frame
+    # axis is merged into the row axis of the store's tensor map; ragged width: clipped by the map)
+    ("up", 2, 32, 48, 256, 256), ("up", 1, 16, 20, 512, 512), ("up", 2, 32, 32, 128, 128),
 ]
 
 

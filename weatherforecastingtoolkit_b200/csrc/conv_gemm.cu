@@ -1145,8 +1145,11 @@ __global__ void __launch_bounds__(conv_threads(HALO, MB), 1)
               __syncwarp();
               if (lane == 0) {
                 const int blk = static_cast<int>(cta_rank) * MB + mb;
-                tma_store_4d(&p.out_map, stg, t.nt * BN + c0, (t.tx * kBlocksPerTile + blk) * 8,
-                             t.ty * 16 + quarter * 4 + ps * (kStRows / 8), t.frame);
+                const int sx = (t.tx * kBlocksPerTile + blk) * 8, sy = t.ty * 16 + quarter * 4 + ps * (kStRows / 8);
+                if (p.use_tma_store == 2)   // sub-pixel phase of the fused upsample: (c, x parity, x, y parity, frame * h + y)
+                  tma_store_5d(&p.out_map, stg, t.nt * BN + c0, t.phase & 1, sx, t.phase >> 1, t.frame * p.tile_h + sy);
+                else
+                  tma_store_4d(&p.out_map, stg, t.nt * BN + c0, sx, sy, t.frame);
                 bulk_commit_group();
               }
             }
@@ -1670,6 +1673,26 @@ extern "C" int wfk_conv_plan_create(const wfk_conv_desc* d, wfk_conv_plan** out)
                                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS) p.use_tma_store = 1;   // otherwise: the per-lane store path
+  }
+  // The four sub-pixel phases of the fused nearest-x2 upsample write every other pixel of every other row. Seen as
+  // (channel, x parity, x, y parity, frame * tile_h + y) the output of ONE phase is a plain 5-D tiled tensor (the frames
+  // merge into the row axis because a frame is exactly tile_h row pairs), so the same 32-channel x 8 x 4|2 pixel boxes
+  // apply. Whole 16-row tiles only: a ragged last tile would spill into the next frame instead of being clipped.
+  static const bool tma_store_up_enabled = !(std::getenv("WFK_TMA_STORE_UP") && std::getenv("WFK_TMA_STORE_UP")[0] == '0');   // A/B switch
+  if (tma_store_enabled && tma_store_up_enabled && plan->halo && !plan->epi && d->out_h != nullptr && d->out_f == nullptr &&
+      d->n_total % plan->bn == 0 && d->num_phases == 4 && d->out_sy == 2 && d->out_sx == 2 && d->out_rows == 2 * d->tile_h &&
+      d->out_cols == 2 * d->tile_w && d->tile_h % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out_h) & 15) == 0) {
+    const cuuint64_t px = static_cast<cuuint64_t>(d->ldc) * 2, row = static_cast<cuuint64_t>(d->out_cols) * px;
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(d->n_total), 2, static_cast<cuuint64_t>(d->tile_w), 2,
+                          static_cast<cuuint64_t>(d->n_frames) * d->tile_h};
+    cuuint64_t strides[4] = {px, 2 * px, row, 2 * row};
+    cuuint32_t box[5] = {32u, 1u, 8u, 1u, plan->bn == 128 ? 4u : 2u};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = wfk::g_encode_tiled(&p.out_map, d->operand_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                     5, d->out_h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) p.use_tma_store = 2;
   }
   const long total_tiles = static_cast<long>(p.num_phases) * p.n_frames * p.tiles_y * p.tiles_x * p.tiles_n;
   if (total_tiles > 0x3fffffffL) {
